@@ -1,0 +1,456 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   C[M, N] = A[M, K] . B[N, K]^T          (A, B fp16 row-major "K-major"; fp32 accumulate)
+//
+// This one kernel carries every dense contraction on the FoundPose hot path:
+//   * ViT patch embedding   (PatchEmbed.proj as a GEMM over 14x14x3 patches,
+//                            reference external/dinov2/dinov2/layers/patch_embed.py:68-81)
+//   * qkv / proj / fc1 / fc2 (external/dinov2/dinov2/layers/attention.py:58,67; mlp.py:35-38)
+//     with bias, exact-erf GELU, and LayerScale*residual fused into the epilogue
+//     (layers/block.py:111-113, layers/layer_scale.py:27)
+//   * PCA projection         (utils/projector_util.py:66-69: X @ C^T - mean @ C^T)
+//
+// Structure (one CTA per SM, 384 threads):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1      : MMA issuer    (tcgen05.mma, 128 x BN x 16 per instruction, accum in TMEM)
+//   warp 2      : TMEM allocator
+//   warps 4..11 : epilogue      (tcgen05.ld -> registers -> fused math -> global)
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i
+// overlaps the main loop of tile i+1.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <stdarg.h>
+
+namespace fp {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B row
+constexpr int kGemmThreads = 384;
+constexpr int kEpilogueWarps = 8;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t kABytes = BM * BK * 2;
+  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 2 * BN;  // 512 or 256: powers of two
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store32(const GemmParams& p, int row, int n0,
+                                                 const uint32_t (&r)[32]) {
+  // One thread owns 32 consecutive output columns [n0, n0+32) of one row.
+  if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
+    __half* dst = p.out_f16 + static_cast<size_t>(row) * p.ld_f16 + n0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+      if (p.bias != nullptr) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 8 + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if constexpr (EPI == EPI_BIAS_GELU_F16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+      }
+      uint4 pk;
+      __half2 h0 = __floats2half2_rn(v[0], v[1]);
+      __half2 h1 = __floats2half2_rn(v[2], v[3]);
+      __half2 h2 = __floats2half2_rn(v[4], v[5]);
+      __half2 h3 = __floats2half2_rn(v[6], v[7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2);
+      pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(dst + j * 8) = pk;
+    }
+  } else if constexpr (EPI == EPI_RESID_F32) {
+    float* dst = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + n0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 x = *reinterpret_cast<float4*>(dst + j * 4);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j * 4));
+      x.x += g.x * (__uint_as_float(r[j * 4 + 0]) + b.x);
+      x.y += g.y * (__uint_as_float(r[j * 4 + 1]) + b.y);
+      x.z += g.z * (__uint_as_float(r[j * 4 + 2]) + b.z);
+      x.w += g.w * (__uint_as_float(r[j * 4 + 3]) + b.w);
+      *reinterpret_cast<float4*>(dst + j * 4) = x;
+    }
+  } else if constexpr (EPI == EPI_PATCH_F32) {
+    const int b_img = row / p.patches_per_img;
+    const int pidx = row - b_img * p.patches_per_img;
+    const size_t drow = static_cast<size_t>(b_img) * p.tokens_per_img + p.tok_off + pidx;
+    float* dst = p.out_f32 + drow * p.ld_f32 + n0;
+    const float* pos = p.pos + static_cast<size_t>(pidx) * p.N + n0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
+      const float4 e = __ldg(reinterpret_cast<const float4*>(pos + j * 4));
+      float4 x;
+      x.x = __uint_as_float(r[j * 4 + 0]) + b.x + e.x;
+      x.y = __uint_as_float(r[j * 4 + 1]) + b.y + e.y;
+      x.z = __uint_as_float(r[j * 4 + 2]) + b.z + e.z;
+      x.w = __uint_as_float(r[j * 4 + 3]) + b.w + e.w;
+      *reinterpret_cast<float4*>(dst + j * 4) = x;
+    }
+  } else {  // EPI_BIAS_F32 (+ optional fp16 copy)
+    float* dst = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + n0;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
+      v[j * 4 + 0] = __uint_as_float(r[j * 4 + 0]) + b.x;
+      v[j * 4 + 1] = __uint_as_float(r[j * 4 + 1]) + b.y;
+      v[j * 4 + 2] = __uint_as_float(r[j * 4 + 2]) + b.z;
+      v[j * 4 + 3] = __uint_as_float(r[j * 4 + 3]) + b.w;
+      *reinterpret_cast<float4*>(dst + j * 4) =
+          make_float4(v[j * 4 + 0], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+    }
+    if (p.out_f16 != nullptr) {
+      __half* d16 = p.out_f16 + static_cast<size_t>(row) * p.ld_f16 + n0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        __half2 h0 = __floats2half2_rn(v[j * 8 + 0], v[j * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(v[j * 8 + 2], v[j * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(v[j * 8 + 4], v[j * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(v[j * 8 + 6], v[j * 8 + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(d16 + j * 8) = pk;
+      }
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], kEpilogueWarps);
+    }
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / num_n;
+        const int n_blk = t - m_blk * num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int sub = warp & 3;            // TMEM subpartition this warp may access
+    const int half = (warp - 4) >> 2;    // which half of the BN columns
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / num_n;
+      const int n_blk = t - m_blk * num_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const int row = m_blk * BM + sub * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int col0 = half * (BN / 2) + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + col0, r);
+        tmem_ld_wait();
+        if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+               cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    FP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  gemm_tn_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI>
+int launch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+              cudaStream_t stream) {
+  if (bn == 256) return launch_one<256, EPI>(tmA, tmB, p, stream);
+  return launch_one<128, EPI>(tmA, tmB, p, stream);
+}
+
+}  // namespace
+
+int gemm_pick_bn(int M, int N) {
+  if (N % 256 != 0) return 128;
+  // Prefer the 128x256 tile unless it quantises badly onto 148 SMs.
+  const long tiles256 = static_cast<long>((M + BM - 1) / BM) * (N / 256);
+  const long waves256 = (tiles256 + kNumSMs - 1) / kNumSMs;
+  const double eff256 = static_cast<double>(tiles256) / (waves256 * kNumSMs);
+  const long tiles128 = tiles256 * 2;
+  const long waves128 = (tiles128 + kNumSMs - 1) / kNumSMs;
+  const double eff128 = static_cast<double>(tiles128) / (waves128 * kNumSMs);
+  return (eff128 > eff256 + 0.04) ? 128 : 256;
+}
+
+int gemm_tn(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
+            cudaStream_t stream) {
+  FP_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_tn: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  FP_REQUIRE(p.N % 128 == 0, "gemm_tn: N=%d must be a multiple of 128", p.N);
+  FP_REQUIRE(p.K % BK == 0, "gemm_tn: K=%d must be a multiple of %d", p.K, BK);
+  FP_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm_tn: leading dimensions must be multiples of 8");
+  FP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             "gemm_tn: operands must be 16-byte aligned");
+  const int bn = gemm_pick_bn(p.M, p.N);
+  CUtensorMap tmA, tmB;
+  if (make_tma_2d_f16(&tmA, A, p.M, p.K, lda, BM) != 0) return 3;
+  if (make_tma_2d_f16(&tmB, B, p.N, p.K, ldb, bn) != 0) return 3;
+  switch (epi) {
+    case EPI_BIAS_F16: return launch_bn<EPI_BIAS_F16>(bn, tmA, tmB, p, stream);
+    case EPI_BIAS_GELU_F16: return launch_bn<EPI_BIAS_GELU_F16>(bn, tmA, tmB, p, stream);
+    case EPI_RESID_F32: return launch_bn<EPI_RESID_F32>(bn, tmA, tmB, p, stream);
+    case EPI_PATCH_F32: return launch_bn<EPI_PATCH_F32>(bn, tmA, tmB, p, stream);
+    case EPI_BIAS_F32: return launch_bn<EPI_BIAS_F32>(bn, tmA, tmB, p, stream);
+    default: set_last_error("gemm_tn: unknown epilogue %d", epi); return 1;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Host: TMA descriptor creation through the runtime-resolved driver entry point.
+// ----------------------------------------------------------------------------
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                             const cuuint64_t*, const cuuint64_t*,
+                                             const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle,
+                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tensorMapEncodeTiled get_encode_fn() {
+  static PFN_tensorMapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+      set_last_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s",
+                     cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_tma_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols) {
+  PFN_tensorMapEncodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return 3;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(__half)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box=%ux%u",
+                   static_cast<int>(r), base, (unsigned long long)rows, (unsigned long long)cols,
+                   (unsigned long long)ld, box_rows, box_cols);
+    return 3;
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// UMMA descriptor probe: a single-CTA, single-tile contraction used by the GPU tests to pin
+// the K-major and MN-major operand descriptors independently of the pipelined kernels.
+//   mode 0: D[128,64] = A[128,64] . B[64(n),64(k)]^T      (B K-major)
+//   mode 1: D[128,64] = A[128,64] . B[64(k),64(n)]        (B MN-major, as V in attention)
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  float* __restrict__ out, int b_mn_major) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sa = smem;            // 128 x 64 fp16 = 16 KB
+  uint8_t* sb = smem + 16384;    // 64 x 64 fp16  =  8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 8192);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bars[0], 16384 + 8192);
+    tma_load_2d(sa, &tmA, &bars[0], 0, 0);
+    tma_load_2d(sb, &tmB, &bars[0], 0, 0);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc_f16(128, 64, 0, b_mn_major);
+    const uint64_t adesc = make_smem_desc_sw128(smem_u32(sa));
+    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sb));
+    for (int k = 0; k < 4; ++k) {
+      // K-major: +32 B per 16-element K step. MN-major: +16 rows x 128 B = 2048 B per K step.
+      const uint64_t boff = b_mn_major ? static_cast<uint64_t>(k) * (2048 >> 4) : 2ull * k;
+      umma_f16_ss(tmem_base, adesc + 2 * k, bdesc + boff, idesc, k != 0);
+    }
+    umma_commit(&bars[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[1], 0);
+  tc_fence_after_sync();
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, r);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) out[row * 64 + c * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+int umma_probe(const __half* A, const __half* B, float* out, int b_mn_major, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  if (make_tma_2d_f16(&tmA, A, 128, 64, 64, 128) != 0) return 3;
+  if (make_tma_2d_f16(&tmB, B, 64, 64, 64, 64) != 0) return 3;
+  const int smem = 16384 + 8192 + 64 + 1024;
+  FP_CUDA_CHECK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smem));
+  umma_probe_kernel<<<1, 128, smem, stream>>>(tmA, tmB, out, b_mn_major);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fp
