@@ -127,3 +127,185 @@ def umma_probe(a: torch.Tensor, b: torch.Tensor, b_mn_major: bool) -> torch.Tens
         "fp_umma_probe",
     )
     return out
+
+
+def _i(v) -> ctypes.c_int:
+    return ctypes.c_int(int(v))
+
+
+def _l(v) -> ctypes.c_int64:
+    return ctypes.c_int64(int(v))
+
+
+def _f(v) -> ctypes.c_float:
+    return ctypes.c_float(float(v))
+
+
+def call(name: str, *args) -> None:
+    """Calls lib.<name>(*args) and raises NativeError on a non-zero status."""
+    check(getattr(load(), name)(*args), name)
+
+
+KNN_ITEM_BYTES = 32  # sizeof(fp_knn_item)
+
+
+def layernorm_f16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    require_cuda(x, "x", torch.float32)
+    m, d = x.shape
+    y = torch.empty((m, d), dtype=torch.float16, device=x.device)
+    call("fp_layernorm_f16", ptr(x), ptr(y), ptr(weight), ptr(bias), _i(m), _i(d), _f(eps), stream_ptr(x.device))
+    return y
+
+
+def attention_f16(qkv: torch.Tensor, batch: int, tokens: int, heads: int) -> torch.Tensor:
+    require_cuda(qkv, "qkv", torch.float16)
+    assert qkv.shape == (batch * tokens, 3 * heads * 64)
+    out = torch.empty((batch * tokens, heads * 64), dtype=torch.float16, device=qkv.device)
+    call("fp_attention_f16", ptr(qkv), ptr(out), _i(batch), _i(tokens), _i(heads), stream_ptr(qkv.device))
+    return out
+
+
+def convert_rows_f16(x: torch.Tensor, l2_normalize: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(x, "x", torch.float32)
+    rows, dim = x.shape
+    if out is None:
+        out = torch.empty((rows, dim), dtype=torch.float16, device=x.device)
+    call("fp_convert_rows_f16", ptr(x), ptr(out), _l(rows), _i(dim), _i(int(l2_normalize)), stream_ptr(x.device))
+    return out
+
+
+def row_sqnorm_f16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(x, "x", torch.float16)
+    rows, dim = x.shape
+    if out is None:
+        out = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    call("fp_row_sqnorm_f16", ptr(x), ptr(out), _l(rows), _i(dim), stream_ptr(x.device))
+    return out
+
+
+def knn_num_items(q_rows: int) -> int:
+    return int(load().fp_knn_num_items(_i(q_rows)))
+
+
+def new_knn_items(num_items: int, device) -> torch.Tensor:
+    """Device buffer holding `num_items` fp_knn_item structs (as int64 words)."""
+    return torch.zeros((max(num_items, 1), KNN_ITEM_BYTES // 8), dtype=torch.int64, device=device)
+
+
+def knn_items_dense(items: torch.Tensor, q_total: int, b_row0: int, b_rows: int) -> None:
+    call("fp_knn_items_dense", ptr(items), _i(q_total), _i(b_row0), _i(b_rows), stream_ptr(items.device))
+
+
+def knn_search_items(q16, q_sqnorm, bank16, bank_sqnorm, items, num_items, metric: int, k: int, out_d, out_i) -> None:
+    require_cuda(q16, "q16", torch.float16)
+    require_cuda(bank16, "bank16", torch.float16)
+    assert q16.shape[1] == bank16.shape[1]
+    call("fp_knn_search_items", ptr(q16), _l(q16.shape[0]), ptr(q_sqnorm), ptr(bank16), _l(bank16.shape[0]),
+         ptr(bank_sqnorm), _i(q16.shape[1]), ptr(items), _i(num_items), _i(metric), _i(k), ptr(out_d), ptr(out_i),
+         stream_ptr(q16.device))
+
+
+def pca_project(x16, comp16, bias, out_f32, out_f16=None) -> None:
+    require_cuda(x16, "x16", torch.float16)
+    require_cuda(comp16, "comp16", torch.float16)
+    m, dd = x16.shape
+    d = comp16.shape[0]
+    call("fp_pca_project", ptr(x16), ptr(comp16), ptr(bias), _i(m), _i(dd), _i(d), ptr(out_f32), ptr(out_f16),
+         stream_ptr(x16.device))
+
+
+def filter_points_by_mask(points, masks_u8, out_points, out_ids, out_counts) -> None:
+    require_cuda(points, "points", torch.float32)
+    require_cuda(masks_u8, "masks", torch.uint8)
+    b, h, w = masks_u8.shape
+    call("fp_filter_points_by_mask", ptr(points), _i(points.shape[0]), ptr(masks_u8), _i(b), _i(h), _i(w),
+         ptr(out_points), ptr(out_ids), ptr(out_counts), _i(out_points.shape[1]), stream_ptr(points.device))
+
+
+def sample_features(tokens, hp, wp, points, counts, img_w, img_h, out_f32=None, out_f16=None) -> None:
+    require_cuda(tokens, "tokens", torch.float32)
+    b = tokens.shape[0]
+    c = tokens.shape[-1]
+    stride = points.shape[1]
+    call("fp_sample_features", ptr(tokens), _i(b), _i(hp), _i(wp), _i(c), ptr(points), ptr(counts), _i(stride),
+         _f(img_w), _f(img_h), ptr(out_f32), ptr(out_f16), stream_ptr(tokens.device))
+
+
+def calc_tfidf(word_ids, word_dists, row_start, row_count, idf, soft: bool, sigma2: float, sqrt_input: bool, out) -> None:
+    require_cuda(word_ids, "word_ids", torch.int64)
+    require_cuda(word_dists, "word_dists", torch.float32)
+    call("fp_calc_tfidf", ptr(word_ids), ptr(word_dists), _i(word_ids.shape[1]), ptr(row_start), ptr(row_count),
+         _i(out.shape[0]), ptr(idf), _i(out.shape[1]), _i(int(soft)), _f(sigma2), _i(int(sqrt_input)), ptr(out),
+         stream_ptr(out.device))
+
+
+def row_norm_f32(x, out=None) -> torch.Tensor:
+    require_cuda(x, "x", torch.float32)
+    if out is None:
+        out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+    call("fp_row_norm_f32", ptr(x), ptr(out), _i(x.shape[0]), _i(x.shape[1]), stream_ptr(x.device))
+    return out
+
+
+def bow_scores(descs, desc_norm, q, out) -> None:
+    require_cuda(descs, "descs", torch.float32)
+    require_cuda(q, "q", torch.float32)
+    call("fp_bow_scores", ptr(descs), ptr(desc_norm), ptr(q), _i(descs.shape[0]), _i(q.shape[0]), _i(descs.shape[1]),
+         ptr(out), stream_ptr(q.device))
+
+
+def topk_rows(x, k: int, out_v, out_i) -> None:
+    require_cuda(x, "x", torch.float32)
+    call("fp_topk_rows", ptr(x), _i(x.shape[0]), _i(x.shape[1]), _i(k), ptr(out_v), ptr(out_i), stream_ptr(x.device))
+
+
+def build_pair_items(top_ids, topn, tpl_off, q_start, q_count, max_q, max_p, items_q2o, items_o2q) -> None:
+    call("fp_build_pair_items", ptr(top_ids), _i(top_ids.numel()), _i(topn), ptr(tpl_off), ptr(q_start), ptr(q_count),
+         _i(max_q), _i(max_p), ptr(items_q2o), ptr(items_o2q), stream_ptr(top_ids.device))
+
+
+def cyclic_buddies(points, q_start, q_count, q2o, o2q, top_ids, topn, tpl_off, feat_perm, vertices, max_q, max_p,
+                   top_k, out_qids, out_vids, out_dists, out_scores, out_c2d, out_c3d, out_count) -> None:
+    call("fp_cyclic_buddies", ptr(points), ptr(q_start), ptr(q_count), ptr(q2o), ptr(o2q), ptr(top_ids),
+         _i(top_ids.numel()), _i(topn), ptr(tpl_off), ptr(feat_perm), ptr(vertices), _i(max_q), _i(max_p), _i(top_k),
+         ptr(out_qids), ptr(out_vids), ptr(out_dists), ptr(out_scores), ptr(out_c2d), ptr(out_c3d), ptr(out_count),
+         stream_ptr(points.device))
+
+
+# ---- ViT handle ---------------------------------------------------------------------------------
+class VitConfig(ctypes.Structure):
+    _fields_ = [("embed_dim", ctypes.c_int), ("num_heads", ctypes.c_int), ("num_blocks", ctypes.c_int),
+                ("num_register_tokens", ctypes.c_int), ("patch_size", ctypes.c_int), ("img_h", ctypes.c_int),
+                ("img_w", ctypes.c_int)]
+
+
+class VitWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("patch_w", "patch_b", "cls_pos", "reg_tokens", "pos_patch", "norm_w", "norm_b")]
+
+
+class VitBlockWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("norm1_w", "norm1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1", "norm2_w", "norm2_b",
+                 "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+
+
+def vit_create(cfg: VitConfig, weights: VitWeights, blocks, max_batch: int) -> ctypes.c_void_p:
+    lib = load()
+    arr = (VitBlockWeights * len(blocks))(*blocks)
+    handle = ctypes.c_void_p(0)
+    check(lib.fp_vit_create(ctypes.byref(cfg), ctypes.byref(weights), arr, _i(max_batch), ctypes.byref(handle)),
+          "fp_vit_create")
+    return handle
+
+
+def vit_destroy(handle: ctypes.c_void_p) -> None:
+    lib = load()
+    lib.fp_vit_destroy.restype = None
+    lib.fp_vit_destroy(handle)
+
+
+def vit_forward(handle, images, layer: int, facet: int, apply_norm: bool, out_tokens, out_tokens_f16, out_cls) -> None:
+    require_cuda(images, "images", torch.float32)
+    call("fp_vit_forward", handle, ptr(images), _i(images.shape[0]), _i(layer), _i(facet), _i(int(apply_norm)),
+         ptr(out_tokens), ptr(out_tokens_f16), ptr(out_cls), stream_ptr(images.device))

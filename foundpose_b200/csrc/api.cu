@@ -49,4 +49,121 @@ int fp_umma_probe(const void* A, const void* B, float* out, int b_mn_major, void
                         b_mn_major, static_cast<cudaStream_t>(stream));
 }
 
+int fp_layernorm_f16(const float* x, void* y_f16, const float* weight, const float* bias, int M,
+                     int D, float eps, void* stream) {
+  return fp::layernorm_f16(x, static_cast<__half*>(y_f16), weight, bias, M, D, eps,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int fp_attention_f16(const void* qkv_f16, void* out_f16, int B, int N, int heads, void* stream) {
+  return fp::attention_f16(static_cast<const __half*>(qkv_f16), static_cast<__half*>(out_f16), B, N,
+                           heads, static_cast<cudaStream_t>(stream));
+}
+
+static_assert(sizeof(fp_knn_item) == sizeof(fp::KnnItem), "fp_knn_item layout mismatch");
+
+int fp_convert_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int l2_normalize,
+                        void* stream) {
+  return fp::convert_rows_f16(x, static_cast<__half*>(y_f16), rows, dim, l2_normalize,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int fp_row_sqnorm_f16(const void* x_f16, float* out, int64_t rows, int dim, void* stream) {
+  return fp::row_sqnorm_f16(static_cast<const __half*>(x_f16), out, rows, dim,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int fp_pca_project(const void* x_f16, const void* components_f16, const float* bias, int M, int D,
+                   int d, float* out_f32, void* out_f16, void* stream) {
+  if (M <= 0) return 0;
+  fp::GemmParams p;
+  p.M = M; p.N = d; p.K = D;
+  p.bias = bias;
+  p.out_f32 = out_f32; p.ld_f32 = d;
+  p.out_f16 = static_cast<__half*>(out_f16); p.ld_f16 = d;
+  return fp::gemm_tn(fp::EPI_BIAS_F32, static_cast<const __half*>(x_f16), D,
+                     static_cast<const __half*>(components_f16), D, p,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int fp_knn_num_items(int q_rows) { return fp::knn_items_per_rows(q_rows); }
+
+int fp_knn_items_dense(fp_knn_item* items, int q_total, int b_row0, int b_rows, void* stream) {
+  return fp::knn_build_items_dense(reinterpret_cast<fp::KnnItem*>(items), q_total, b_row0, b_rows,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_sqnorm,
+                        const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
+                        int dim, const fp_knn_item* items, int num_items, int metric, int k,
+                        float* out_d, int64_t* out_i, void* stream) {
+  if (metric != 0 && metric != 1) {
+    fp::set_last_error("Metric %d is not supported.", metric);
+    return 1;
+  }
+  return fp::knn_search_items(static_cast<const __half*>(q_f16), q_rows_total,
+                              static_cast<const __half*>(bank_f16), bank_rows_total, dim,
+                              reinterpret_cast<const fp::KnnItem*>(items), num_items, q_sqnorm,
+                              bank_sqnorm, metric, k, out_d, out_i,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int fp_filter_points_by_mask(const float* points, int num_points, const uint8_t* masks, int B,
+                             int H, int W, float* out_points, int32_t* out_ids,
+                             int32_t* out_counts, int out_stride, void* stream) {
+  return fp::filter_points_by_mask(points, num_points, masks, B, H, W, out_points, out_ids,
+                                   out_counts, out_stride, static_cast<cudaStream_t>(stream));
+}
+
+int fp_sample_features(const float* tokens, int B, int Hp, int Wp, int C, const float* points,
+                       const int32_t* counts, int stride, float img_w, float img_h, float* out_f32,
+                       void* out_f16, void* stream) {
+  return fp::sample_features(tokens, B, Hp, Wp, C, points, counts, stride, img_w, img_h, out_f32,
+                             static_cast<__half*>(out_f16), static_cast<cudaStream_t>(stream));
+}
+
+int fp_calc_tfidf(const int64_t* word_ids, const float* word_dists, int k,
+                  const int32_t* row_start, const int32_t* row_count, int B, const float* idf,
+                  int W, int soft_assignment, float soft_sigma_squared, int sqrt_input, float* out,
+                  void* stream) {
+  return fp::tfidf_histogram(word_ids, word_dists, k, row_start, row_count, B, idf, W,
+                             soft_assignment, soft_sigma_squared, sqrt_input, out,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int fp_row_norm_f32(const float* x, float* out, int rows, int dim, void* stream) {
+  return fp::row_norm_f32(x, out, rows, dim, static_cast<cudaStream_t>(stream));
+}
+
+int fp_bow_scores(const float* descs, const float* desc_norm, const float* q, int T, int B, int W,
+                  float* out, void* stream) {
+  return fp::bow_scores(descs, desc_norm, q, T, B, W, out, static_cast<cudaStream_t>(stream));
+}
+
+int fp_topk_rows(const float* x, int rows, int cols, int k, float* out_v, int64_t* out_i,
+                 void* stream) {
+  return fp::topk_rows(x, rows, cols, k, out_v, out_i, static_cast<cudaStream_t>(stream));
+}
+
+int fp_build_pair_items(const int64_t* top_ids, int num_pairs, int topn, const int32_t* tpl_off,
+                        const int32_t* q_start, const int32_t* q_count, int max_q, int max_p,
+                        fp_knn_item* items_q2o, fp_knn_item* items_o2q, void* stream) {
+  return fp::build_pair_items(top_ids, num_pairs, topn, tpl_off, q_start, q_count, max_q, max_p,
+                              reinterpret_cast<fp::KnnItem*>(items_q2o),
+                              reinterpret_cast<fp::KnnItem*>(items_o2q),
+                              static_cast<cudaStream_t>(stream));
+}
+
+int fp_cyclic_buddies(const float* points, const int32_t* q_start, const int32_t* q_count,
+                      const int64_t* q2o, const int64_t* o2q, const int64_t* top_ids,
+                      int num_pairs, int topn, const int32_t* tpl_off, const int64_t* feat_perm,
+                      const float* vertices, int max_q, int max_p, int top_k, int64_t* out_query_ids,
+                      int64_t* out_vertex_ids, float* out_dists, float* out_scores,
+                      float* out_coord_2d, float* out_coord_3d, int32_t* out_count, void* stream) {
+  return fp::cyclic_buddies(points, q_start, q_count, q2o, o2q, top_ids, num_pairs, topn, tpl_off,
+                            feat_perm, vertices, max_q, max_p, top_k, out_query_ids, out_vertex_ids,
+                            out_dists, out_scores, out_coord_2d, out_coord_3d, out_count,
+                            static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

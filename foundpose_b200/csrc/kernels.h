@@ -38,4 +38,69 @@ int gemm_tn(int epi, const __half* A, int lda, const __half* B, int ldb, const G
             cudaStream_t stream);
 int umma_probe(const __half* A, const __half* B, float* out, int b_mn_major, cudaStream_t stream);
 
+
+// ---- vit_ops.cu -------------------------------------------------------------------------
+int patchify_normalize(const float* img, __half* out, int B, int H, int W, int ps, int Kpad,
+                       cudaStream_t stream);
+int init_special_tokens(float* x, const float* cls_pos, const float* reg, int B, int ntok, int R,
+                        int D, cudaStream_t stream);
+int layernorm_f16(const float* x, __half* y, const float* w, const float* b, int M, int D, float eps,
+                  cudaStream_t stream);
+int final_norm_tokens(const float* x, const float* w, const float* b, float* out_tok,
+                      __half* out_tok16, float* out_cls, int B, int ntok, int R, int P, int D,
+                      int apply_norm, float eps, cudaStream_t stream);
+
+// ---- attention_tcgen05.cu ---------------------------------------------------------------
+int attention_f16(const __half* qkv, __half* out, int B, int N, int heads, cudaStream_t stream);
+
+
+// ---- knn_tcgen05.cu ---------------------------------------------------------------------
+// One k-NN work item: query rows [q_row0, q_row0+q_rows) (q_rows <= 128) against bank rows
+// [b_row0, b_row0+b_rows); results go to output rows [out_row0, out_row0+q_rows); returned
+// indices are relative to b_row0. Mirrors fp_knn_item in the public header.
+struct KnnItem {
+  int q_row0;
+  int q_rows;
+  int b_row0;
+  int b_rows;
+  long long out_row0;
+  long long pad;
+};
+int knn_items_per_rows(int rows);
+int knn_build_items_dense(KnnItem* items, int q_total, int b_row0, int b_rows, cudaStream_t stream);
+int row_sqnorm_f16(const __half* x, float* out, long rows, int dim, cudaStream_t stream);
+int convert_rows_f16(const float* x, __half* y, long rows, int dim, int l2_normalize,
+                     cudaStream_t stream);
+int knn_search_items(const __half* q, long q_rows_total, const __half* x, long x_rows_total, int dim,
+                     const KnnItem* items, int num_items, const float* qnorm, const float* xnorm,
+                     int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream);
+
+
+// ---- feature_ops.cu ---------------------------------------------------------------------
+int filter_points_by_mask(const float* points, int num_points, const uint8_t* masks, int B, int H,
+                          int W, float* out_points, int* out_ids, int* out_counts, int out_stride,
+                          cudaStream_t stream);
+int sample_features(const float* tokens, int B, int Hp, int Wp, int C, const float* points,
+                    const int* counts, int stride, float img_w, float img_h, float* out_f32,
+                    __half* out_f16, cudaStream_t stream);
+
+// ---- retrieval.cu -----------------------------------------------------------------------
+int tfidf_histogram(const int64_t* word_ids, const float* word_dists, int k, const int* row_start,
+                    const int* row_count, int B, const float* idf, int W, int soft, float sigma2,
+                    int sqrt_input, float* out, cudaStream_t stream);
+int row_norm_f32(const float* x, float* out, int rows, int dim, cudaStream_t stream);
+int bow_scores(const float* descs, const float* desc_norm, const float* q, int T, int B, int W,
+               float* out, cudaStream_t stream);
+int topk_rows(const float* x, int rows, int cols, int k, float* out_v, int64_t* out_i,
+              cudaStream_t stream);
+int build_pair_items(const int64_t* top_ids, int num_pairs, int topn, const int* tpl_off,
+                     const int* q_start, const int* q_count, int max_q, int max_p,
+                     KnnItem* items_q2o, KnnItem* items_o2q, cudaStream_t stream);
+int cyclic_buddies(const float* points, const int* q_start, const int* q_count, const int64_t* q2o,
+                   const int64_t* o2q, const int64_t* top_ids, int num_pairs, int topn,
+                   const int* tpl_off, const int64_t* feat_perm, const float* vertices, int max_q,
+                   int max_p, int top_k, int64_t* out_qids, int64_t* out_vids, float* out_dists,
+                   float* out_scores, float* out_c2d, float* out_c3d, int* out_count,
+                   cudaStream_t stream);
+
 }  // namespace fp

@@ -1,0 +1,353 @@
+// Brute-force k-NN (squared L2 / inner product) on tcgen05 with a running top-k epilogue.
+//
+// Replaces faiss.IndexFlatL2.search / IndexFlatIP.search as called from utils/knn_util.py:83,95
+// (faiss 1.8.0, CPU).  faiss evaluates ||q||^2 + ||x||^2 - 2<q,x> with an sgemm; here the <q,x>
+// tile is a tcgen05.mma (fp16 operands, fp32 accumulate in TMEM) and the epilogue keeps the k best
+// candidates of each query in registers while the bank streams through shared memory - the
+// distance matrix never exists in HBM.
+//
+// Work is described by "items": one item = up to 128 consecutive query rows searched against one
+// contiguous segment of bank rows.  That covers every k-NN on the path with one kernel:
+//   K1  all queries  vs the visual-word centroids           (utils/template_util.py:13-29)
+//   K2  a crop's queries vs one template's rows             (utils/corresp_util.py:46)
+//   K3  a template's rows vs a crop's queries               (utils/corresp_util.py:47)
+//   K4  queries vs the full bank                            (BASELINE.json configs 3, 5)
+// Items may be produced on the device (knn_build_items_*), so the retrieval pipeline needs no
+// host synchronisation.
+//
+// CTA layout (256 threads, persistent over items):
+//   warp 0   TMA producer   (query k-block + bank-tile k-block per stage, 128B swizzle)
+//   warp 1   MMA issuer     (128 x 128 x 16 tcgen05.mma, accumulators double-buffered in TMEM)
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue      (thread = query row: tcgen05.ld dots, d = ||x||^2 - 2 dot, sorted insert)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fp {
+
+namespace {
+
+constexpr int BQ = 128;   // query rows per item
+constexpr int BX = 128;   // bank rows per tile
+constexpr int BKK = 64;   // K elements per stage
+constexpr int kStages = 6;
+constexpr uint32_t kQStage = BQ * BKK * 2;
+constexpr uint32_t kXStage = BX * BKK * 2;
+constexpr uint32_t kStageBytes = kQStage + kXStage;
+constexpr uint32_t kKnnSmem = kStages * kStageBytes + 256 + 1024;
+constexpr int kKnnThreads = 256;
+
+template <int K>
+struct TopK {
+  float d[K];
+  int i[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < K; ++j) { d[j] = INFINITY; i[j] = -1; }
+  }
+  // Sorted ascending; a later candidate with an equal distance never displaces an earlier one,
+  // so ties resolve to the lower index (candidates arrive in ascending index order).
+  __device__ __forceinline__ void push(float cd, int ci) {
+    if (cd < d[K - 1]) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (cd < d[j]) {
+          const float td = d[j]; d[j] = cd; cd = td;
+          const int ti = i[j]; i[j] = ci; ci = ti;
+        }
+      }
+    }
+  }
+};
+
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads, 1)
+knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
+           const KnnItem* __restrict__ items, int num_items, int dim,
+           const float* __restrict__ qnorm, const float* __restrict__ xnorm, int metric_ip,
+           int k_out, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 2 * BX);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = dim / BKK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+        const KnnItem item = items[it];
+        if (item.q_rows <= 0 || item.b_rows <= 0) continue;
+        const int num_tiles = (item.b_rows + BX - 1) / BX;
+        for (int t = 0; t < num_tiles; ++t) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sq = smem + stage * kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_2d(sq, &tmQ, &full_bar[stage], kb * BKK, item.q_row0);
+            tma_load_2d(sq + kQStage, &tmX, &full_bar[stage], kb * BKK, item.b_row0 + t * BX);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BQ, BX);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+        const KnnItem item = items[it];
+        if (item.q_rows <= 0 || item.b_rows <= 0) continue;
+        const int num_tiles = (item.b_rows + BX - 1) / BX;
+        for (int t = 0; t < num_tiles; ++t) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + acc * BX;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t sq = smem_u32(smem + stage * kStageBytes);
+            const uint64_t adesc = make_smem_desc_sw128(sq);
+            const uint64_t bdesc = make_smem_desc_sw128(sq + kQStage);
+#pragma unroll
+            for (int k = 0; k < BKK / 16; ++k)
+              umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int sub = warp & 3;
+    const int r = sub * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      const KnnItem item = items[it];
+      if (item.q_rows <= 0 || item.b_rows <= 0) continue;
+      const int num_tiles = (item.b_rows + BX - 1) / BX;
+      TopK<K> best;
+      best.init();
+      for (int t = 0; t < num_tiles; ++t) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after_sync();
+        const int col_base = t * BX;
+        const int ncols = min(BX, item.b_rows - col_base);
+        const float* xn = xnorm + item.b_row0 + col_base;
+#pragma unroll 1
+        for (int c = 0; c < BX / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * BX + c * 32, v);
+          tmem_ld_wait();
+          if (c * 32 < ncols) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = c * 32 + i;
+              if (col < ncols) {
+                const float dot = __uint_as_float(v[i]);
+                // L2: ||x||^2 - 2<q,x> (||q||^2 is added once at the end); IP: -<q,x>.
+                const float cand = metric_ip ? -dot : fmaf(-2.0f, dot, __ldg(xn + col));
+                best.push(cand, col_base + col);
+              }
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (r < item.q_rows) {
+        const long row = static_cast<long>(item.out_row0) + r;
+        const float qn = metric_ip ? 0.f : qnorm[static_cast<long>(item.q_row0) + r];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          if (j < k_out) {
+            float dv;
+            if (metric_ip) dv = -best.d[j];                 // similarity, descending
+            else dv = fmaxf(best.d[j] + qn, 0.f);           // faiss clamps negative distances to 0
+            if (best.i[j] < 0) dv = metric_ip ? -INFINITY : INFINITY;  // fewer than k bank rows
+            out_d[row * k_out + j] = dv;
+            out_i[row * k_out + j] = best.i[j];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 2 * BX);
+  }
+}
+
+template <int K>
+int launch_knn(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* items, int num_items,
+               int dim, const float* qnorm, const float* xnorm, int metric_ip, int k_out,
+               float* out_d, int64_t* out_i, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    FP_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kKnnSmem));
+    configured = true;
+  }
+  const int grid = num_items < kNumSMs ? num_items : kNumSMs;
+  knn_kernel<K><<<grid, kKnnThreads, kKnnSmem, stream>>>(tmQ, tmX, items, num_items, dim, qnorm,
+                                                        xnorm, metric_ip, k_out, out_d, out_i);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ||row||^2 in fp32 of fp16 rows: one warp per row.
+__global__ void row_sqnorm_kernel(const __half* __restrict__ x, float* __restrict__ out, long rows,
+                                  int dim) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long row = blockIdx.x * static_cast<long>(wpb) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long>(gridDim.x) * wpb) {
+    const __half2* p = reinterpret_cast<const __half2*>(x + row * dim);
+    float s = 0.f;
+    for (int i = lane; i < dim / 2; i += 32) {
+      const float2 f = __half22float2(p[i]);
+      s = fmaf(f.x, f.x, s);
+      s = fmaf(f.y, f.y, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = s;
+  }
+}
+
+// fp32 -> fp16 row conversion with optional L2 normalisation (cosine metric,
+// utils/knn_util.py:57, 93) - one warp per row.
+__global__ void convert_rows_kernel(const float* __restrict__ x, __half* __restrict__ y, long rows,
+                                    int dim, int l2_normalize) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long row = blockIdx.x * static_cast<long>(wpb) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long>(gridDim.x) * wpb) {
+    const float* xr = x + row * dim;
+    float inv = 1.f;
+    if (l2_normalize) {
+      float s = 0.f;
+      for (int i = lane; i < dim; i += 32) s = fmaf(xr[i], xr[i], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      inv = 1.0f / sqrtf(s);
+    }
+    for (int i = lane; i < dim; i += 32) y[row * dim + i] = __float2half_rn(xr[i] * inv);
+  }
+}
+
+// Items for one dense problem: all query rows against one bank segment.
+__global__ void build_items_dense_kernel(KnnItem* items, int num_items, int q_total, int b_row0,
+                                         int b_rows) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_items; i += gridDim.x * blockDim.x) {
+    KnnItem it;
+    it.q_row0 = i * BQ;
+    it.q_rows = min(BQ, q_total - i * BQ);
+    it.b_row0 = b_row0;
+    it.b_rows = b_rows;
+    it.out_row0 = static_cast<long long>(i) * BQ;
+    it.pad = 0;
+    items[i] = it;
+  }
+}
+
+}  // namespace
+
+int knn_items_per_rows(int rows) { return (rows + BQ - 1) / BQ; }
+
+int knn_build_items_dense(KnnItem* items, int q_total, int b_row0, int b_rows, cudaStream_t stream) {
+  const int n = knn_items_per_rows(q_total);
+  if (n == 0) return 0;
+  build_items_dense_kernel<<<(n + 255) / 256, 256, 0, stream>>>(items, n, q_total, b_row0, b_rows);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int row_sqnorm_f16(const __half* x, float* out, long rows, int dim, cudaStream_t stream) {
+  if (rows == 0) return 0;
+  FP_REQUIRE(dim % 2 == 0, "row_sqnorm: dim must be even");
+  long blocks = (rows + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  row_sqnorm_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, out, rows, dim);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int convert_rows_f16(const float* x, __half* y, long rows, int dim, int l2_normalize,
+                     cudaStream_t stream) {
+  if (rows == 0) return 0;
+  long blocks = (rows + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  convert_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, rows, dim, l2_normalize);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int knn_search_items(const __half* q, long q_rows_total, const __half* x, long x_rows_total, int dim,
+                     const KnnItem* items, int num_items, const float* qnorm, const float* xnorm,
+                     int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream) {
+  FP_REQUIRE(k >= 1 && k <= 16, "knn: k=%d is outside the supported range [1,16]", k);
+  FP_REQUIRE(dim % BKK == 0 && dim >= BKK, "knn: dim=%d must be a positive multiple of %d", dim, BKK);
+  if (num_items <= 0 || q_rows_total <= 0) return 0;
+  FP_REQUIRE(x_rows_total > 0, "knn: the index is empty");
+  CUtensorMap tmQ, tmX;
+  if (make_tma_2d_f16(&tmQ, q, q_rows_total, dim, dim, BQ) != 0) return 3;
+  if (make_tma_2d_f16(&tmX, x, x_rows_total, dim, dim, BX) != 0) return 3;
+#define FP_KNN_CASE(KK)                                                                          \
+  return launch_knn<KK>(tmQ, tmX, items, num_items, dim, qnorm, xnorm, metric_ip, k, out_d, out_i, \
+                        stream)
+  if (k == 1) FP_KNN_CASE(1);
+  if (k == 2) FP_KNN_CASE(2);
+  if (k == 3) FP_KNN_CASE(3);
+  if (k <= 5) FP_KNN_CASE(5);
+  if (k <= 8) FP_KNN_CASE(8);
+  FP_KNN_CASE(16);
+#undef FP_KNN_CASE
+}
+
+}  // namespace fp

@@ -1,0 +1,228 @@
+// Memory-bound helper kernels of the ViT stage (everything that is not a contraction).
+//
+//   patchify_normalize : images fp32 [B,3,H,W] in [0,1]  -> fp16 im2col rows [B*P, Kpad]
+//                        with the ImageNet normalisation of utils/dinov2_utils.py:111-113,123 fused
+//                        (PatchEmbed.proj is a 14x14/14 conv = GEMM over these rows,
+//                        external/dinov2/dinov2/layers/patch_embed.py:75)
+//   init_special_tokens: cls (+pos[0]) and register rows of the token stream
+//                        (models/vision_transformer.py:219-230)
+//   layernorm_f16      : LayerNorm(eps=1e-6) fp32 residual stream -> fp16 GEMM operand
+//                        (layers/block.py:63,75)
+//   final_norm_tokens  : drop cls/register tokens, final LayerNorm over [cls | patches]
+//                        (utils/dinov2_utils.py:126-153), fp32 + optional fp16 copy
+//
+// All of them are HBM-bound streaming kernels: one warp per row, 128-bit accesses, grid sized
+// from the row count.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fp {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One thread per (patch, k-chunk of 14 contiguous pixels = one row of one channel of the patch).
+__global__ void patchify_normalize_kernel(const float* __restrict__ img, __half* __restrict__ out,
+                                          int B, int H, int W, int ps, int Kpad) {
+  const int Hp = H / ps, Wp = W / ps;
+  const int rows_per_patch = 3 * ps;  // (channel, dy) pairs
+  const long total = static_cast<long>(B) * Hp * Wp * rows_per_patch;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(idx % rows_per_patch);
+    const long patch = idx / rows_per_patch;
+    const int c = r / ps, dy = r - c * ps;
+    const int px = static_cast<int>(patch % Wp);
+    const int py = static_cast<int>((patch / Wp) % Hp);
+    const int b = static_cast<int>(patch / (static_cast<long>(Wp) * Hp));
+    const float* src = img + ((static_cast<long>(b) * 3 + c) * H + (py * ps + dy)) * W + px * ps;
+    __half* dst = out + patch * Kpad + c * ps * ps + dy * ps;
+    // (x - mean) / std exactly as torchvision's normalize (sub then div).
+    for (int dx = 0; dx < ps; ++dx) dst[dx] = __float2half_rn((src[dx] - mean[c]) / stdv[c]);
+    if (r == 0) {
+      for (int k = 3 * ps * ps; k < Kpad; ++k) out[patch * Kpad + k] = __float2half_rn(0.f);
+    }
+  }
+}
+
+// x[b, 0, :] = cls_pos ; x[b, 1..R, :] = reg[r]
+__global__ void init_special_tokens_kernel(float* __restrict__ x, const float* __restrict__ cls_pos,
+                                           const float* __restrict__ reg, int B, int ntok, int R,
+                                           int D) {
+  const long total = static_cast<long>(B) * (1 + R) * D;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(idx % D);
+    const int t = static_cast<int>((idx / D) % (1 + R));
+    const int b = static_cast<int>(idx / (static_cast<long>(D) * (1 + R)));
+    const float v = (t == 0) ? cls_pos[d] : reg[static_cast<long>(t - 1) * D + d];
+    x[(static_cast<long>(b) * ntok + t) * D + d] = v;
+  }
+}
+
+// LayerNorm over D (multiple of 128, <= 2048): one warp per row, row cached in registers.
+template <int MAX_VEC>
+__device__ __forceinline__ void ln_row(const float* __restrict__ xr, int D, const float* __restrict__ w,
+                                       const float* __restrict__ bvec, float eps, int lane,
+                                       float4 (&v)[MAX_VEC], int& nvec) {
+  nvec = D / 128;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (i < nvec) {
+      v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (i < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (i < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w + (i * 32 + lane) * 4));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(bvec + (i * 32 + lane) * 4));
+      v[i].x = (v[i].x - mean) * rstd * g.x + be.x;
+      v[i].y = (v[i].y - mean) * rstd * g.y + be.y;
+      v[i].z = (v[i].z - mean) * rstd * g.z + be.z;
+      v[i].w = (v[i].w - mean) * rstd * g.w + be.w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, const float* __restrict__ w,
+                     const float* __restrict__ b, int M, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long row = blockIdx.x * static_cast<long>(warps_per_block) + (threadIdx.x >> 5); row < M;
+       row += static_cast<long>(gridDim.x) * warps_per_block) {
+    float4 v[16];
+    int nvec;
+    ln_row<16>(x + row * D, D, w, b, eps, lane, v, nvec);
+    __half* yr = y + row * D;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < nvec) {
+        __half2 h0 = __floats2half2_rn(v[i].x, v[i].y);
+        __half2 h1 = __floats2half2_rn(v[i].z, v[i].w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(yr + (i * 32 + lane) * 4) = pk;
+      }
+    }
+  }
+}
+
+// Output row j of image b: j == 0 -> cls token (row b*ntok), j >= 1 -> patch token
+// (row b*ntok + 1 + R + j - 1). Optional LayerNorm. Writes cls to out_cls[b], patches to
+// out_tok[b*P + j-1] (fp32) and out_tok16 (fp16, optional).
+__global__ void __launch_bounds__(256)
+final_norm_tokens_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                         const float* __restrict__ bvec, float* __restrict__ out_tok,
+                         __half* __restrict__ out_tok16, float* __restrict__ out_cls, int B,
+                         int ntok, int R, int P, int D, int apply_norm, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long total = static_cast<long>(B) * (P + 1);
+  for (long o = blockIdx.x * static_cast<long>(warps_per_block) + (threadIdx.x >> 5); o < total;
+       o += static_cast<long>(gridDim.x) * warps_per_block) {
+    const int b = static_cast<int>(o / (P + 1));
+    const int j = static_cast<int>(o - static_cast<long>(b) * (P + 1));
+    const long src_row = static_cast<long>(b) * ntok + (j == 0 ? 0 : R + j);
+    float4 v[16];
+    int nvec = D / 128;
+    if (apply_norm) {
+      ln_row<16>(x + src_row * D, D, w, bvec, eps, lane, v, nvec);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvec) v[i] = *reinterpret_cast<const float4*>(x + src_row * D + (i * 32 + lane) * 4);
+    }
+    float* dst = (j == 0) ? (out_cls != nullptr ? out_cls + static_cast<long>(b) * D : nullptr)
+                          : out_tok + (static_cast<long>(b) * P + (j - 1)) * D;
+    if (dst != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvec) *reinterpret_cast<float4*>(dst + (i * 32 + lane) * 4) = v[i];
+    }
+    if (j > 0 && out_tok16 != nullptr) {
+      __half* d16 = out_tok16 + (static_cast<long>(b) * P + (j - 1)) * D;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < nvec) {
+          __half2 h0 = __floats2half2_rn(v[i].x, v[i].y);
+          __half2 h1 = __floats2half2_rn(v[i].z, v[i].w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(d16 + (i * 32 + lane) * 4) = pk;
+        }
+      }
+    }
+  }
+}
+
+inline int grid_for(long work_items, int per_block, int max_blocks = kNumSMs * 8) {
+  long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  return static_cast<int>(g > max_blocks ? max_blocks : g);
+}
+
+}  // namespace
+
+int patchify_normalize(const float* img, __half* out, int B, int H, int W, int ps, int Kpad,
+                       cudaStream_t stream) {
+  FP_REQUIRE(H % ps == 0, "Input image height %d is not a multiple of patch height %d", H, ps);
+  FP_REQUIRE(W % ps == 0, "Input image width %d is not a multiple of patch width: %d", W, ps);
+  FP_REQUIRE(Kpad >= 3 * ps * ps, "patchify: Kpad too small");
+  const long total = static_cast<long>(B) * (H / ps) * (W / ps) * 3 * ps;
+  patchify_normalize_kernel<<<grid_for(total, 256), 256, 0, stream>>>(img, out, B, H, W, ps, Kpad);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int init_special_tokens(float* x, const float* cls_pos, const float* reg, int B, int ntok, int R,
+                        int D, cudaStream_t stream) {
+  const long total = static_cast<long>(B) * (1 + R) * D;
+  init_special_tokens_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, cls_pos, reg, B, ntok, R, D);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_f16(const float* x, __half* y, const float* w, const float* b, int M, int D, float eps,
+                  cudaStream_t stream) {
+  FP_REQUIRE(D % 128 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 128 and <= 2048", D);
+  layernorm_f16_kernel<<<grid_for(M, 8), 256, 0, stream>>>(x, y, w, b, M, D, eps);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int final_norm_tokens(const float* x, const float* w, const float* b, float* out_tok,
+                      __half* out_tok16, float* out_cls, int B, int ntok, int R, int P, int D,
+                      int apply_norm, float eps, cudaStream_t stream) {
+  FP_REQUIRE(D % 128 == 0 && D <= 2048, "final_norm: D=%d must be a multiple of 128 and <= 2048", D);
+  const long total = static_cast<long>(B) * (P + 1);
+  final_norm_tokens_kernel<<<grid_for(total, 8), 256, 0, stream>>>(x, w, b, out_tok, out_tok16,
+                                                                  out_cls, B, ntok, R, P, D,
+                                                                  apply_norm, eps);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fp

@@ -1,0 +1,99 @@
+"""Brute-force k-NN on the B200 - drop-in for the reference's utils/knn_util.py (faiss wrapper).
+
+`KNN(k, metric).fit(data)` / `.search(data) -> (distances [N,k] fp32, indices [N,k] int64)` with the
+semantics the reference obtains from faiss.IndexFlatL2 / IndexFlatIP (utils/knn_util.py:38-106):
+metric "l2" returns SQUARED L2 distances in ascending order; metric "cosine" L2-normalises both sides
+and returns 1 - cosine similarity.  Rows are stored in fp16 with fp32 ||x||^2 (north-star layout);
+the search is `fp_knn_search_items` (tcgen05 distance tiles + register top-k).  Results are returned
+on the device of the query tensor, as the reference does (:102-104).
+"""
+
+from typing import Any, Optional, Tuple
+
+import torch
+
+from foundpose_b200 import _native
+
+_MAX_K = 16
+
+
+def _device_for(t: torch.Tensor) -> torch.device:
+    return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+
+def _pad64(x: torch.Tensor) -> torch.Tensor:
+    d = x.shape[1]
+    dp = (d + 63) // 64 * 64
+    x = x.to(torch.float32)
+    if dp != d:
+        x = torch.nn.functional.pad(x, (0, dp - d))
+    return x.contiguous()
+
+
+class KNN:
+    """K nearest neighbor search."""
+
+    def __init__(self, k: int = 1, metric: str = "l2", radius: Optional[float] = None,
+                 res: Optional[Any] = None) -> None:
+        self.index: Any = None
+        self.k: int = k
+        self.metric: str = metric
+        self.radius: Optional[float] = radius
+        self.res: Optional[Any] = res
+        self._bank16: Optional[torch.Tensor] = None
+        self._bank_sqnorm: Optional[torch.Tensor] = None
+
+    @classmethod
+    def from_packed(cls, bank16: torch.Tensor, bank_sqnorm: torch.Tensor, k: int = 1, metric: str = "l2") -> "KNN":
+        """An index over already packed fp16 rows (a zero-copy view of an ObjectIndex segment)."""
+        self = cls(k=k, metric=metric)
+        self._bank16, self._bank_sqnorm = bank16, bank_sqnorm
+        self.index = self
+        return self
+
+    def fit(self, data: torch.Tensor) -> None:
+        """Creates index from provided vectors of shape (num_vectors, dimensionality)."""
+        if self.metric not in ("l2", "cosine"):
+            raise ValueError(f"Metric {self.metric} is not supported.")
+        dev = _device_for(data)
+        x = _pad64(data.detach().to(dev))
+        self._bank16 = _native.convert_rows_f16(x, l2_normalize=(self.metric == "cosine"))
+        self._bank_sqnorm = _native.row_sqnorm_f16(self._bank16)
+        self.index = self
+
+    def search(self, data: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Finds nearest neighbors; returns (distances, indices) of the k nearest neighbors."""
+        if self.metric not in ("l2", "cosine"):
+            raise ValueError(f"Metric {self.metric} is not supported.")
+        if self.radius is not None:
+            # The reference calls index.range_search_with_radius, which faiss does not provide
+            # (dead code).
+            raise NotImplementedError("radius search is dead code in the reference and is not provided")
+        if self._bank16 is None:
+            raise RuntimeError("KNN.fit must be called before KNN.search")
+        if self.k > _MAX_K:
+            raise NotImplementedError(f"k={self.k} > {_MAX_K} is not supported by the B200 k-NN kernel")
+        out_device = data.device
+        dev = self._bank16.device
+        q = _pad64(data.detach().to(dev))
+        nq = q.shape[0]
+        dist = torch.empty((nq, self.k), dtype=torch.float32, device=dev)
+        idx = torch.empty((nq, self.k), dtype=torch.int64, device=dev)
+        if nq > 0:
+            cosine = self.metric == "cosine"
+            q16 = _native.convert_rows_f16(q, l2_normalize=cosine)
+            qn = _native.row_sqnorm_f16(q16)
+            n_items = _native.knn_num_items(nq)
+            items = _native.new_knn_items(n_items, dev)
+            _native.knn_items_dense(items, nq, 0, self._bank16.shape[0])
+            _native.knn_search_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_items,
+                                     1 if cosine else 0, self.k, dist, idx)
+            if cosine:
+                dist = 1.0 - dist  # cosine similarity -> cosine distance (reference :98)
+        return dist.to(out_device), idx.to(out_device)
+
+    def serialize_index(self) -> None:
+        pass
+
+    def deserialize_index(self) -> None:
+        pass

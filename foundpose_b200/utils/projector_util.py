@@ -1,0 +1,141 @@
+"""PCA projection of descriptors - mirror of the reference's utils/projector_util.py.
+
+`PCAProjector.transform` evaluates X @ C^T - mean @ C^T (what sklearn's PCA.transform computes with
+whiten=False, reference :66-69) as a tcgen05 GEMM with the bias -(mean @ C^T) fused into the
+epilogue (`fp_pca_project`).  `fit` is offline (gen_repre) and stays on scikit-learn.
+"""
+
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from foundpose_b200 import _native
+from foundpose_b200.utils import logging
+from foundpose_b200.utils.misc import array_to_tensor, tensor_to_array
+
+logger: logging.Logger = logging.get_logger()
+
+
+class Projector:
+    """An abstract class for a projector."""
+
+    def fit(self, data_x: torch.Tensor, data_y: Optional[torch.Tensor] = None, **kwargs: Any) -> None:
+        raise NotImplementedError
+
+    def transform(self, data_x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+
+class _PCAState:
+    """Minimal stand-in for a fitted sklearn PCA (attribute names follow scikit-learn)."""
+
+    def __init__(self, n_components: int, whiten: bool = False) -> None:
+        self.n_components = n_components
+        self.whiten = whiten
+        self.components_ = None
+        self.mean_ = None
+        self.explained_variance_ = None
+        self.explained_variance_ratio_ = None
+        self.singular_values_ = None
+        self.noise_variance_ = None
+
+
+class PCAProjector(Projector):
+    def __init__(self, n_components: int, whiten: bool = False, **kwargs: Dict[str, Any]) -> None:
+        self.n_components: int = n_components
+        self.whiten: bool = whiten
+        self.pca: Any = _PCAState(n_components=n_components, whiten=whiten)
+        self._device_state: Dict[str, Dict[str, torch.Tensor]] = {}
+
+    def fit(self, data_x: torch.Tensor, data_y: Optional[torch.Tensor] = None, **kwargs: Any) -> None:
+        """Offline (scripts/gen_repre.py:272-284): delegated to scikit-learn like the reference."""
+        from sklearn.decomposition import PCA
+
+        if "max_samples" in kwargs:
+            if data_x.shape[0] > kwargs["max_samples"]:
+                perm = torch.randperm(data_x.shape[0])
+                data_x = data_x[perm[: kwargs["max_samples"]]]
+        self.pca = PCA(n_components=self.n_components, whiten=self.whiten)
+        self.pca.fit(tensor_to_array(data_x))
+        self._device_state = {}
+
+    def device_state(self, device: torch.device) -> Dict[str, torch.Tensor]:
+        """fp16 components (rows padded to a multiple of 128) and the fused bias on `device`."""
+        key = str(device)
+        if key not in self._device_state:
+            if bool(np.asarray(getattr(self.pca, "whiten", False)).any()):
+                raise NotImplementedError("whitened PCA never occurs after projector_from_tensordict")
+            comp = torch.as_tensor(np.asarray(self.pca.components_), dtype=torch.float32)
+            mean = torch.as_tensor(np.asarray(self.pca.mean_), dtype=torch.float32)
+            d_out, d_in = comp.shape
+            assert d_in % 64 == 0, f"input feature dim {d_in} must be a multiple of 64"
+            d_pad = (d_out + 127) // 128 * 128
+            comp_p = torch.zeros(d_pad, d_in)
+            comp_p[:d_out] = comp
+            bias = torch.zeros(d_pad)
+            bias[:d_out] = -(mean.reshape(1, -1).numpy() @ comp.numpy().T).reshape(-1)
+            self._device_state[key] = {
+                "components16": comp_p.to(device, torch.float16).contiguous(),
+                "bias": bias.to(device).contiguous(),
+                "d_out": d_out,
+            }
+        return self._device_state[key]
+
+    def transform(self, data_x: torch.Tensor) -> torch.Tensor:
+        if not data_x.is_cuda:
+            raise ValueError("foundpose_b200 runs on CUDA tensors only (no CPU fallback)")
+        st = self.device_state(data_x.device)
+        x16 = _native.convert_rows_f16(data_x.to(torch.float32).contiguous())
+        m = x16.shape[0]
+        d_pad = st["components16"].shape[0]
+        out = torch.empty((m, d_pad), dtype=torch.float32, device=data_x.device)
+        if m > 0:
+            _native.pca_project(x16, st["components16"], st["bias"], out, None)
+        return out[:, : st["d_out"]]
+
+
+def project_features(feat_vectors: torch.Tensor, projectors: List[Projector], batch_size: int = 4096) -> torch.Tensor:
+    """Projects (num_features, feat_dims) feature vectors with every projector in turn."""
+    for projector in projectors:
+        feat_vectors = projector.transform(feat_vectors)
+    return feat_vectors
+
+
+def projector_to_tensordict(projector: Projector) -> Dict[str, Any]:
+    """Converts a feature projector to a tensordict (same keys as the reference :91-113)."""
+    if isinstance(projector, PCAProjector):
+        return {
+            "pca_projector": {
+                "components": torch.tensor(np.asarray(projector.pca.components_)),
+                "explained_variance": torch.tensor(np.asarray(projector.pca.explained_variance_)),
+                "explained_variance_ratio": torch.tensor(np.asarray(projector.pca.explained_variance_ratio_)),
+                "singular_values": torch.tensor(np.asarray(projector.pca.singular_values_)),
+                "mean": torch.tensor(np.asarray(projector.pca.mean_)),
+                "noise_variance": torch.tensor(np.asarray(projector.pca.noise_variance_)),
+                "whiten": torch.tensor(projector.whiten),
+            }
+        }
+    else:
+        raise ValueError(f"Unknown projector type: {type(projector)}")
+
+
+def projector_from_tensordict(projector_dict: Dict[str, Any]) -> Projector:
+    """Builds a projector from a tensordict (reference :116-145)."""
+    if "pca_projector" in projector_dict:
+        p = projector_dict["pca_projector"]
+        pca = _PCAState(n_components=len(p["components"]))
+        pca.components_ = tensor_to_array(p["components"])
+        pca.explained_variance_ = tensor_to_array(p["explained_variance"])
+        pca.explained_variance_ratio_ = tensor_to_array(p["explained_variance_ratio"])
+        pca.singular_values_ = tensor_to_array(p["singular_values"])
+        pca.mean_ = tensor_to_array(p["mean"])
+        pca.noise_variance_ = tensor_to_array(p["noise_variance"])
+        pca.whiten_ = tensor_to_array(p["whiten"])
+        # As in the reference, `whiten` stays False after loading (PCA(...) is rebuilt with defaults).
+        projector = PCAProjector(n_components=len(pca.components_), whiten=False)
+        projector.whiten = pca.whiten_
+        projector.pca = pca
+        return projector
+    else:
+        raise ValueError("Unknown projector type.")

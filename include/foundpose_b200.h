@@ -46,6 +46,163 @@ int fp_gemm_tn_f16(int epilogue, const void* A, int lda, const void* B, int ldb,
 /* Single-tile UMMA descriptor probe used by the GPU tests (not on the hot path). */
 int fp_umma_probe(const void* A, const void* B, float* out, int b_mn_major, void* stream);
 
+/* ---- ViT building blocks (exported for unit tests; fp_vit_forward sequences them) -------- */
+/* LayerNorm(eps) over the last dimension: x fp32 [M,D] -> y f16 [M,D].
+ * Replaces torch layer_norm at external/dinov2/dinov2/layers/block.py:63,75. D % 128 == 0. */
+int fp_layernorm_f16(const float* x, void* y_f16, const float* weight, const float* bias, int M,
+                     int D, float eps, void* stream);
+
+/* Fused softmax(q k^T / sqrt(64)) v for all heads (head_dim 64): qkv f16 [B*N, 3*heads*64]
+ * (columns [q|k|v], each head-major) -> out f16 [B*N, heads*64].
+ * Replaces the bmm/softmax/bmm of external/dinov2/dinov2/layers/attention.py:60-66. */
+int fp_attention_f16(const void* qkv_f16, void* out_f16, int B, int N, int heads, void* stream);
+
+/* ---- DINOv2 feature extractor -------------------------------------------------------------
+ * Replaces DinoFeatureExtractor.forward (utils/dinov2_utils.py:115-158) = ImageNet normalise +
+ * DinoVisionTransformer blocks 0..layer (external/dinov2/dinov2/models/vision_transformer.py:
+ * 213-232, 254-270; layers/block.py:89-114) + final LayerNorm over [cls | patch] tokens. */
+typedef struct fp_vit fp_vit; /* opaque */
+
+typedef struct {
+  int embed_dim;            /* D: 384 / 768 / 1024; must equal num_heads * 64 */
+  int num_heads;
+  int num_blocks;           /* number of blocks whose weights are supplied (>= layer + 1) */
+  int num_register_tokens;  /* 0 or 4 */
+  int patch_size;           /* 14 */
+  int img_h, img_w;         /* multiples of patch_size */
+} fp_vit_config;
+
+typedef struct {            /* device pointers; the caller keeps them alive while the handle lives */
+  const void* patch_w;      /* f16 [D, Kpad]: PatchEmbed.proj.weight flattened (c,dy,dx), zero padded
+                               to Kpad = fp_vit_patch_k() columns */
+  const float* patch_b;     /* [D] */
+  const float* cls_pos;     /* [D]  cls_token + pos_embed[0] */
+  const float* reg_tokens;  /* [R, D] or NULL */
+  const float* pos_patch;   /* [P, D] positional embedding resampled to the patch grid
+                               (interpolate_pos_encoding, vision_transformer.py:179-211; done once
+                               per image size by the host) */
+  const float* norm_w;      /* [D] final LayerNorm */
+  const float* norm_b;
+} fp_vit_weights;
+
+typedef struct {            /* one transformer block; weights f16 [out, in], vectors fp32 */
+  const float* norm1_w; const float* norm1_b;
+  const void* qkv_w;  const float* qkv_b;    /* [3D, D], [3D] */
+  const void* proj_w; const float* proj_b;   /* [D, D],  [D]  */
+  const float* ls1;                          /* [D] LayerScale gamma */
+  const float* norm2_w; const float* norm2_b;
+  const void* fc1_w; const float* fc1_b;     /* [4D, D], [4D] */
+  const void* fc2_w; const float* fc2_b;     /* [D, 4D], [D]  */
+  const float* ls2;
+} fp_vit_block_weights;
+
+/* Allocates the activation workspace for up to max_batch images. */
+int fp_vit_create(const fp_vit_config* cfg, const fp_vit_weights* weights,
+                  const fp_vit_block_weights* blocks, int max_batch, fp_vit** out);
+void fp_vit_destroy(fp_vit* handle);
+/* Padded length of one flattened patch (columns of patch_w). */
+int fp_vit_patch_k(const fp_vit* handle);
+/* images fp32 [B,3,H,W] in [0,1] -> out_tokens fp32 [B, P, D] (patch tokens of block `layer`,
+ * row-major over the patch grid; feature_maps = out_tokens viewed as B x Hp x Wp x D),
+ * optional f16 copy, optional out_cls fp32 [B, D].
+ * facet: 0 token, 1 query, 2 key, 3 value (utils/dinov2_utils.py:160-196). */
+int fp_vit_forward(fp_vit* handle, const float* images, int batch, int layer, int facet,
+                   int apply_norm, float* out_tokens, void* out_tokens_f16, float* out_cls,
+                   void* stream);
+
+/* ---- descriptor conversion ---------------------------------------------------------------- */
+/* fp32 rows -> f16 rows, optionally L2-normalised first (cosine metric: utils/knn_util.py:57,93). */
+int fp_convert_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int l2_normalize,
+                        void* stream);
+/* out[r] = ||x[r]||^2 (fp32) of f16 rows; the ||x||^2 term of faiss's L2 expansion. */
+int fp_row_sqnorm_f16(const void* x_f16, float* out, int64_t rows, int dim, void* stream);
+
+/* ---- PCA projection ------------------------------------------------------------------------
+ * out = x . components^T + bias, bias = -(mean . components^T)  (sklearn PCA.transform with
+ * whiten=False as called at utils/projector_util.py:66-69).  x f16 [M,D], components f16 [d,D],
+ * d % 128 == 0, D % 64 == 0.  Writes fp32 [M,d] and, if out_f16 != NULL, an f16 copy (the k-NN
+ * operand). */
+int fp_pca_project(const void* x_f16, const void* components_f16, const float* bias, int M, int D,
+                   int d, float* out_f32, void* out_f16, void* stream);
+
+/* ---- brute-force k-NN ----------------------------------------------------------------------
+ * Replaces faiss.IndexFlatL2.search / IndexFlatIP.search (utils/knn_util.py:83, 95).
+ * One item = <=128 consecutive query rows against one contiguous run of bank rows; indices are
+ * returned relative to b_row0 (a per-template index in the reference, scripts/infer.py:224-239). */
+typedef struct {
+  int32_t q_row0, q_rows;   /* query rows [q_row0, q_row0 + q_rows), q_rows <= 128 (0 = skip) */
+  int32_t b_row0, b_rows;   /* bank rows  [b_row0, b_row0 + b_rows) */
+  int64_t out_row0;         /* results go to output rows [out_row0, out_row0 + q_rows) */
+  int64_t reserved;
+} fp_knn_item;
+
+/* Number of items that cover q_rows query rows of one dense problem. */
+int fp_knn_num_items(int q_rows);
+/* Fills items[0 .. fp_knn_num_items(q_total)) for "all query rows vs bank rows [b_row0, +b_rows)". */
+int fp_knn_items_dense(fp_knn_item* items, int q_total, int b_row0, int b_rows, void* stream);
+/* metric 0: squared L2, ascending (out_d = max(||q||^2 + ||x||^2 - 2<q,x>, 0));
+ * metric 1: inner product, descending (out_d = <q,x>).  k <= 16, dim % 64 == 0.
+ * q_sqnorm / bank_sqnorm: fp_row_sqnorm_f16 of the respective rows (unused for metric 1).
+ * out_d fp32 [rows,k], out_i int64 [rows,k]; ties resolve to the lower index. */
+int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_sqnorm,
+                        const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
+                        int dim, const fp_knn_item* items, int num_items, int metric, int k,
+                        float* out_d, int64_t* out_i, void* stream);
+
+/* ---- query points and feature sampling ---------------------------------------------------- */
+/* filter_points_by_mask (utils/feature_util.py:75-97) for B crops sharing one point grid:
+ * keeps points whose rounded pixel lies strictly inside the canvas and inside masks[b] (uint8,
+ * [B,H,W]); order preserved.  Outputs use a fixed stride of out_stride (>= num_points) rows per
+ * crop: out_points fp32 [B,out_stride,2], out_ids int32 [B,out_stride], out_counts int32 [B]. */
+int fp_filter_points_by_mask(const float* points, int num_points, const uint8_t* masks, int B,
+                             int H, int W, float* out_points, int32_t* out_ids,
+                             int32_t* out_counts, int out_stride, void* stream);
+/* sample_feature_map_at_points (utils/feature_util.py:100-131): bilinear grid_sample,
+ * align_corners=False, zero padding.  tokens fp32 [B, Hp*Wp, C] (token-major feature map);
+ * points fp32 [B,stride,2] image coordinates; counts int32 [B] or NULL (= stride).  Rows past
+ * counts[b] are zero-filled.  Writes fp32 and/or f16 [B*stride, C]. */
+int fp_sample_features(const float* tokens, int B, int Hp, int Wp, int C, const float* points,
+                       const int32_t* counts, int stride, float img_w, float img_h, float* out_f32,
+                       void* out_f16, void* stream);
+
+/* ---- tf-idf bag-of-words template retrieval ----------------------------------------------- */
+/* calc_tfidf (utils/template_util.py:31-71) for B crops: rows [row_start[b], +row_count[b]) of
+ * word_ids int64 [*,k] / word_dists fp32 [*,k] -> out fp32 [B,W].  sqrt_input=1 applies the sqrt
+ * of template_util.py:27 to word_dists first (query side). */
+int fp_calc_tfidf(const int64_t* word_ids, const float* word_dists, int k,
+                  const int32_t* row_start, const int32_t* row_count, int B, const float* idf,
+                  int W, int soft_assignment, float soft_sigma_squared, int sqrt_input, float* out,
+                  void* stream);
+/* out[r] = ||x[r]|| (fp32 rows). */
+int fp_row_norm_f32(const float* x, float* out, int rows, int dim, void* stream);
+/* torch.nn.functional.cosine_similarity(template_descs, tile(query_tfidf)) for B crops at once
+ * (utils/template_util.py:167-169): descs fp32 [T,W], desc_norm [T], q fp32 [B,W] -> out [B,T]. */
+int fp_bow_scores(const float* descs, const float* desc_norm, const float* q, int T, int B, int W,
+                  float* out, void* stream);
+/* torch.topk(x, k, sorted=True) per row (utils/template_util.py:172-174), ties -> lower index. */
+int fp_topk_rows(const float* x, int rows, int cols, int k, float* out_v, int64_t* out_i,
+                 void* stream);
+
+/* ---- cyclic-buddies correspondences -------------------------------------------------------- */
+/* k-NN work items of the two 1-NN searches per (crop, retrieved template) pair
+ * (utils/corresp_util.py:46-47).  pair p = b * topn + j uses template top_ids[p];
+ * items_q2o: ceil(max_q/128) items per pair (crop queries vs template rows, results at rows
+ * p*max_q + i); items_o2q: ceil(max_p/128) items per pair (template rows vs crop queries,
+ * results at rows p*max_p + o).  tpl_off int32 [T+1] = CSR offsets of the templates' bank rows. */
+int fp_build_pair_items(const int64_t* top_ids, int num_pairs, int topn, const int32_t* tpl_off,
+                        const int32_t* q_start, const int32_t* q_count, int max_q, int max_p,
+                        fp_knn_item* items_q2o, fp_knn_item* items_o2q, void* stream);
+/* cyclic_buddies_matching + the gathers of establish_correspondences
+ * (utils/corresp_util.py:50-68, 135-155) for every pair; outputs have top_k rows per pair, the
+ * first out_count[p] = min(top_k, q_count[b]) are valid, ordered by (cycle distance, query id).
+ * feat_perm (int64, may be NULL) maps sorted bank rows back to original feature ids. */
+int fp_cyclic_buddies(const float* points, const int32_t* q_start, const int32_t* q_count,
+                      const int64_t* q2o, const int64_t* o2q, const int64_t* top_ids,
+                      int num_pairs, int topn, const int32_t* tpl_off, const int64_t* feat_perm,
+                      const float* vertices, int max_q, int max_p, int top_k, int64_t* out_query_ids,
+                      int64_t* out_vertex_ids, float* out_dists, float* out_scores,
+                      float* out_coord_2d, float* out_coord_3d, int32_t* out_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,125 @@
+"""GPU parity of the ViT stage (A1-A4) against the CPU oracle and the golden reference outputs.
+
+The CUDA path computes GEMM operands in fp16 with fp32 accumulation and an fp32 residual stream;
+the oracle is fp32 throughout, so bit-exactness is not defined for this stage (SURVEY.md §7 "Hard
+parts").  Tolerances (stated per test): relative Frobenius error and per-token cosine similarity.
+"""
+import os
+
+import pytest
+import torch
+
+from foundpose_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+GOLD_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.pt")
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_layernorm_matches_torch():
+    from foundpose_b200 import _native
+
+    g = torch.Generator().manual_seed(0)
+    for d in (128, 384, 1024):
+        x = (torch.randn(1000, d, generator=g) * 3 + 0.5).cuda()
+        w = torch.randn(d, generator=g).cuda()
+        b = torch.randn(d, generator=g).cuda()
+        y = _native.layernorm_f16(x, w, b, 1e-6).float()
+        ref = torch.nn.functional.layer_norm(x, (d,), w, b, 1e-6)
+        assert (y - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("batch,tokens,heads", [(1, 128, 1), (2, 17, 2), (3, 901, 16), (2, 905, 6), (1, 257, 2)])
+def test_attention_matches_torch(batch, tokens, heads):
+    """fp16 Q/K/V, fp32 softmax: |err| <= 2e-3 * max|ref| (P is rounded to fp16 before P@V)."""
+    from foundpose_b200 import _native
+
+    g = torch.Generator().manual_seed(1)
+    d = heads * 64
+    qkv = (torch.randn(batch * tokens, 3 * d, generator=g) * 1.5).half().cuda()
+    out = _native.attention_f16(qkv, batch, tokens, heads).float()
+    q, k, v = qkv.float().reshape(batch, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    attn = ((q * 64 ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
+    ref = (attn @ v).transpose(1, 2).reshape(batch * tokens, d)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("arch_name", ["tiny-test", "tiny-test-reg"])
+def test_vit_tiny_vs_golden_and_oracle(arch_name):
+    from foundpose_b200.utils import dinov2_utils
+    from oracle import vit as ovit
+
+    gold = torch.load(GOLD_PATH, weights_only=False)
+    meta = gold[f"vit/{arch_name}/meta"]
+    arch = synthetic.VIT_ARCHS[arch_name]
+    sd = synthetic.make_vit_state_dict(arch, seed=meta["wseed"])
+    images = synthetic.make_crops(2, (meta["size"], meta["size"]), seed=meta["iseed"])
+    name = f"dinov2_version={arch_name}_stride=14_facet=token_layer={meta['layer']}_norm=1"
+    ext = dinov2_utils.DinoFeatureExtractor(name, state_dict=sd).to("cuda")
+    out = ext(images.cuda())
+    ref = gold[f"vit/{arch_name}/feature_maps"]
+    assert out["feature_maps"].shape == ref.shape
+    # fp16 operands vs fp32 reference: relative Frobenius error <= 5e-3 after <= 3 blocks.
+    assert _rel(out["feature_maps"].cpu(), ref) <= 5e-3
+    assert _rel(out["cls_tokens"].cpu(), gold[f"vit/{arch_name}/cls_tokens"]) <= 5e-3
+    for facet in ("key", "value"):
+        ext.facet = facet
+        outf = ext(images.cuda())
+        assert _rel(outf["feature_maps"].cpu(), gold[f"vit/{arch_name}/feature_maps_{facet}"]) <= 5e-3
+    ext.facet = "token"
+    # norm=0 variant against the oracle.
+    ext.apply_norm = False
+    o2 = ext(images.cuda())
+    r2 = ovit.extract(sd, arch, images, layer=meta["layer"], apply_norm=False)
+    assert _rel(o2["feature_maps"].cpu(), r2["feature_maps"]) <= 5e-3
+
+
+@pytest.mark.parametrize("tag,batch", [("vits14-reg", 2), ("vitl14", 2)])
+def test_vit_real_arch_vs_oracle(tag, batch):
+    """ViT-S/14-reg and ViT-L/14 at 420x420, layer 9, against the fp32 CPU oracle (10 blocks).
+
+    Tolerance: relative Frobenius error <= 1e-2, min per-token cosine similarity >= 0.9995.
+    """
+    from foundpose_b200.utils import dinov2_utils
+    from oracle import vit as ovit
+
+    gold = torch.load(GOLD_PATH, weights_only=False)
+    meta = gold[f"vit/{tag}/meta"]
+    opts = ovit.parse_extractor_name(meta["name"])
+    arch = synthetic.VIT_ARCHS[opts["version"]]
+    sd = synthetic.make_vit_state_dict(arch, seed=meta["wseed"], depth=opts["layer"] + 1)
+    images = torch.cat([synthetic.make_crops(1, (420, 420), seed=meta["iseed"]),
+                        synthetic.make_crops(batch - 1, (420, 420), seed=77)])
+    ext = dinov2_utils.DinoFeatureExtractor(meta["name"], state_dict=sd).to("cuda")
+    out = ext(images.cuda())
+    fm = out["feature_maps"].cpu()
+    assert fm.shape == (batch, arch.embed_dim, 30, 30)
+    # crop 0 against the golden output of the reference's own modules
+    assert _rel(fm[:1, ::8, ::3, ::3], gold[f"vit/{tag}/feature_maps_sub"]) <= 1e-2
+    ref = ovit.extract(sd, arch, images, layer=opts["layer"], num_blocks=opts["layer"] + 1)["feature_maps"]
+    assert _rel(fm, ref) <= 1e-2
+    a = fm.permute(0, 2, 3, 1).reshape(-1, arch.embed_dim)
+    b = ref.permute(0, 2, 3, 1).reshape(-1, arch.embed_dim)
+    cos = torch.nn.functional.cosine_similarity(a, b, dim=1)
+    print(f"{tag}: rel err {_rel(fm, ref):.2e}, min cos {cos.min().item():.6f}")
+    assert cos.min().item() >= 0.9995
+
+
+def test_extractor_errors():
+    from foundpose_b200.utils import dinov2_utils, feature_util
+
+    arch = synthetic.VIT_ARCHS["tiny-test"]
+    sd = synthetic.make_vit_state_dict(arch, seed=1)
+    with pytest.raises(AssertionError):
+        dinov2_utils.DinoFeatureExtractor("dino_tiny-test", state_dict=sd)
+    with pytest.raises(NotImplementedError):
+        feature_util.make_feature_extractor("resnet50")
+    ext = dinov2_utils.DinoFeatureExtractor("dinov2_version=tiny-test_layer=1", state_dict=sd).to("cuda")
+    with pytest.raises(AssertionError):  # H, W must be multiples of 14 (patch_embed.py:72-73)
+        ext(torch.rand(1, 3, 50, 56, device="cuda"))
+    with pytest.raises(ValueError):      # no CPU fallback
+        ext(torch.rand(1, 3, 56, 56))
