@@ -100,6 +100,9 @@ def make_vit_state_dict(arch: VitArch, seed: int = 0, depth: Optional[int] = Non
     k = 3 * arch.patch_size * arch.patch_size
     sd["patch_embed.proj.weight"] = nrm(d, 3, arch.patch_size, arch.patch_size, std=1.0 / math.sqrt(k))
     sd["patch_embed.proj.bias"] = nrm(d, std=0.02)
+    # Drawn before the blocks so that a depth-truncated state dict is a prefix-consistent subset.
+    norm_w = nrm(d, std=0.1, mean=1.0)
+    norm_b = nrm(d, std=0.05)
     for i in range(n_blocks):
         p = f"blocks.{i}."
         sd[p + "norm1.weight"] = nrm(d, std=0.1, mean=1.0)
@@ -116,8 +119,8 @@ def make_vit_state_dict(arch: VitArch, seed: int = 0, depth: Optional[int] = Non
         sd[p + "mlp.fc2.weight"] = tn(d, hidden)
         sd[p + "mlp.fc2.bias"] = nrm(d, std=0.02)
         sd[p + "ls2.gamma"] = nrm(d, std=0.1, mean=0.8)
-    sd["norm.weight"] = nrm(d, std=0.1, mean=1.0)
-    sd["norm.bias"] = nrm(d, std=0.05)
+    sd["norm.weight"] = norm_w
+    sd["norm.bias"] = norm_b
     return sd
 
 

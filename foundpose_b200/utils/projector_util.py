@@ -74,7 +74,7 @@ class PCAProjector(Projector):
             comp_p = torch.zeros(d_pad, d_in)
             comp_p[:d_out] = comp
             bias = torch.zeros(d_pad)
-            bias[:d_out] = -(mean.reshape(1, -1).numpy() @ comp.numpy().T).reshape(-1)
+            bias[:d_out] = torch.from_numpy(-(mean.reshape(1, -1).numpy() @ comp.numpy().T).reshape(-1))
             self._device_state[key] = {
                 "components16": comp_p.to(device, torch.float16).contiguous(),
                 "bias": bias.to(device).contiguous(),

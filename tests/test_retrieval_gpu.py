@@ -84,7 +84,7 @@ def test_knn_l2_vs_oracle(nq, nb, dim, k):
     margin = oknn.topk_margin(q, bank, k)
     sure = margin > 1e-4
     assert torch.equal(i.cpu()[sure], ri[sure]), "index mismatch outside the tie margin"
-    assert sure.float().mean().item() > 0.99
+    assert sure.float().mean().item() > 0.95
     ok = torch.isfinite(rd)
     assert ((d.cpu() - rd).abs()[ok] <= 1e-3 * rd.abs()[ok] + 1e-4).all()   # 1e-3 relative (north_star)
     assert bool((d[:, 1:] >= d[:, :-1]).all())
