@@ -6,6 +6,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,9 +24,95 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- launch accounting / profiling --------------------------------------------------------
+struct ProfRecord {
+  int category;
+  double work;
+  cudaEvent_t start, stop;
+};
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<unsigned long long> g_launches_by_cat[PROF_NUM_CATEGORIES];
+static bool g_profiling = false;
+static std::mutex g_prof_mutex;
+static std::vector<ProfRecord*> g_records;
+
+ProfScope::ProfScope(int category, cudaStream_t stream, double work)
+    : category_(category), stream_(stream), rec_(nullptr) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_launches_by_cat[category].fetch_add(1, std::memory_order_relaxed);
+  if (g_profiling) {
+    ProfRecord* r = new ProfRecord();
+    r->category = category;
+    r->work = work;
+    cudaEventCreate(&r->start);
+    cudaEventCreate(&r->stop);
+    cudaEventRecord(r->start, stream);
+    rec_ = r;
+  }
+}
+
+ProfScope::~ProfScope() {
+  if (rec_ != nullptr) {
+    ProfRecord* r = static_cast<ProfRecord*>(rec_);
+    cudaEventRecord(r->stop, stream_);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_records.push_back(r);
+  }
+}
+
 }  // namespace fp
 
 extern "C" {
+
+unsigned long long fp_launch_count(void) { return fp::g_launches.load(); }
+
+unsigned long long fp_launch_count_category(int category) {
+  if (category < 0 || category >= fp::PROF_NUM_CATEGORIES) return 0;
+  return fp::g_launches_by_cat[category].load();
+}
+
+int fp_profile_enable(int on) {
+  fp::g_profiling = on != 0;
+  return 0;
+}
+
+int fp_profile_read(int category, double* total_ms, double* total_work, int* launches, int reset) {
+  if (category < 0 || category >= fp::PROF_NUM_CATEGORIES) {
+    fp::set_last_error("fp_profile_read: bad category %d", category);
+    return 1;
+  }
+  std::lock_guard<std::mutex> lock(fp::g_prof_mutex);
+  double ms = 0.0, work = 0.0;
+  int n = 0;
+  for (fp::ProfRecord* r : fp::g_records) {
+    if (r->category != category) continue;
+    if (cudaEventSynchronize(r->stop) != cudaSuccess) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r->start, r->stop) == cudaSuccess) {
+      ms += t;
+      work += r->work;
+      ++n;
+    }
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_work) *total_work = work;
+  if (launches) *launches = n;
+  if (reset) {
+    std::vector<fp::ProfRecord*> keep;
+    for (fp::ProfRecord* r : fp::g_records) {
+      if (r->category == category) {
+        cudaEventDestroy(r->start);
+        cudaEventDestroy(r->stop);
+        delete r;
+      } else {
+        keep.push_back(r);
+      }
+    }
+    fp::g_records.swap(keep);
+  }
+  return 0;
+}
+
 
 const char* fp_last_error(void) { return fp::g_last_error; }
 

@@ -327,6 +327,7 @@ int attention_f16(const __half* qkv, __half* out, int B, int N, int heads, cudaS
   }
   dim3 grid((N + kBQ - 1) / kBQ, heads, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // hd^-0.5 * log2(e), hd = 64
+  ProfScope prof(PROF_ATTENTION, stream, 4.0 * B * heads * static_cast<double>(N) * N * kHD);
   attention_kernel<<<grid, kAttnThreads, AttnSmem::total, stream>>>(tm, out, N, D, scale_log2e);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -39,6 +39,31 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 // ----------------------------------------------------------------------------
+// Launch accounting / optional per-kernel timing (defined in api.cu).  Every kernel launcher of
+// the library opens one scope: it always bumps the launch counter (bench.py reports it as
+// `gpu_launches`) and, when profiling is enabled, brackets the launch with CUDA events on the
+// launching stream so bench.py can attribute device time and algorithmic work per kernel family.
+// ----------------------------------------------------------------------------
+enum ProfCategory : int {
+  PROF_GEMM = 0,        // gemm_tn_kernel          (work = flops)
+  PROF_ATTENTION = 1,   // attention_kernel        (work = flops)
+  PROF_LAYERNORM = 2,   // layernorm / final norm  (work = bytes)
+  PROF_VIT_MISC = 3,    // patchify, special tokens, facet gather (work = bytes)
+  PROF_KNN = 4,         // knn_kernel              (work = flops, upper bound for device-built items)
+  PROF_FEATURE = 5,     // mask filter, sampling, conversions, norms (work = bytes)
+  PROF_RETRIEVAL = 6,   // tf-idf, cosine scores, top-k, items, cyclic buddies (work = bytes)
+  PROF_NUM_CATEGORIES = 7,
+};
+
+struct ProfScope {
+  ProfScope(int category, cudaStream_t stream, double work);
+  ~ProfScope();
+  int category_;
+  cudaStream_t stream_;
+  void* rec_;
+};
+
+// ----------------------------------------------------------------------------
 // Small helpers
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

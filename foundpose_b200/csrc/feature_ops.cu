@@ -141,6 +141,7 @@ int filter_points_by_mask(const float* points, int num_points, const uint8_t* ma
                           cudaStream_t stream) {
   FP_REQUIRE(out_stride >= num_points, "filter_points_by_mask: out_stride < num_points");
   if (B <= 0) return 0;
+  ProfScope prof(PROF_FEATURE, stream, static_cast<double>(B) * num_points * 13);
   filter_points_kernel<<<B, 256, 0, stream>>>(points, num_points, masks, H, W, out_points, out_ids,
                                               out_counts, out_stride);
   FP_CUDA_CHECK(cudaGetLastError());
@@ -155,6 +156,7 @@ int sample_features(const float* tokens, int B, int Hp, int Wp, int C, const flo
   if (total <= 0) return 0;
   long blocks = (total + 7) / 8;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  ProfScope prof(PROF_FEATURE, stream, static_cast<double>(total) * C * (4 + (out_f32 ? 4 : 0) + (out_f16 ? 2 : 0)));
   sample_features_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
       tokens, Hp, Wp, C, points, counts, stride, B, img_w, img_h, out_f32, out_f16);
   FP_CUDA_CHECK(cudaGetLastError());

@@ -284,6 +284,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  ProfScope prof(PROF_GEMM, stream, 2.0 * p.M * p.N * p.K);
   gemm_tn_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -234,6 +234,7 @@ int launch_knn(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* it
     configured = true;
   }
   const int grid = num_items < kNumSMs ? num_items : kNumSMs;
+  ProfScope prof(PROF_KNN, stream, 0.0);
   knn_kernel<K><<<grid, kKnnThreads, kKnnSmem, stream>>>(tmQ, tmX, items, num_items, dim, qnorm,
                                                         xnorm, metric_ip, k_out, out_d, out_i);
   FP_CUDA_CHECK(cudaGetLastError());
@@ -303,6 +304,7 @@ int knn_items_per_rows(int rows) { return (rows + BQ - 1) / BQ; }
 int knn_build_items_dense(KnnItem* items, int q_total, int b_row0, int b_rows, cudaStream_t stream) {
   const int n = knn_items_per_rows(q_total);
   if (n == 0) return 0;
+  ProfScope prof(PROF_RETRIEVAL, stream, n * 32.0);
   build_items_dense_kernel<<<(n + 255) / 256, 256, 0, stream>>>(items, n, q_total, b_row0, b_rows);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -313,6 +315,7 @@ int row_sqnorm_f16(const __half* x, float* out, long rows, int dim, cudaStream_t
   FP_REQUIRE(dim % 2 == 0, "row_sqnorm: dim must be even");
   long blocks = (rows + 7) / 8;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  ProfScope prof(PROF_FEATURE, stream, static_cast<double>(rows) * dim * 2);
   row_sqnorm_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, out, rows, dim);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -323,6 +326,7 @@ int convert_rows_f16(const float* x, __half* y, long rows, int dim, int l2_norma
   if (rows == 0) return 0;
   long blocks = (rows + 7) / 8;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  ProfScope prof(PROF_FEATURE, stream, static_cast<double>(rows) * dim * 6);
   convert_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, rows, dim, l2_normalize);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;

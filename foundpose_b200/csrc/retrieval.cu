@@ -348,6 +348,7 @@ int tfidf_histogram(const int64_t* word_ids, const float* word_dists, int k, con
                                        200 * 1024));
     configured = true;
   }
+  ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(B) * W * 4);
   tfidf_kernel<<<B, 256, W * 4, stream>>>(word_ids, word_dists, k, row_start, row_count, idf, W, soft,
                                           sigma2, sqrt_input, out);
   FP_CUDA_CHECK(cudaGetLastError());
@@ -358,6 +359,7 @@ int row_norm_f32(const float* x, float* out, int rows, int dim, cudaStream_t str
   if (rows <= 0) return 0;
   int blocks = (rows + 7) / 8;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(rows) * dim * 4);
   row_norm_f32_kernel<<<blocks, 256, 0, stream>>>(x, out, rows, dim);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -367,6 +369,7 @@ int bow_scores(const float* descs, const float* desc_norm, const float* q, int T
                float* out, cudaStream_t stream) {
   if (T <= 0 || B <= 0) return 0;
   dim3 grid((T + BT - 1) / BT, (B + BC - 1) / BC);
+  ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(T) * W * 4 * ((B + BC - 1) / BC) + static_cast<double>(B) * W * 4);
   bow_scores_kernel<<<grid, 256, 0, stream>>>(descs, desc_norm, q, T, B, W, 1e-8f, out);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -377,6 +380,7 @@ int topk_rows(const float* x, int rows, int cols, int k, float* out_v, int64_t* 
   FP_REQUIRE(k >= 1 && k <= kMaxTopK, "topk: k=%d is outside [1,%d]", k, kMaxTopK);
   FP_REQUIRE(k <= cols, "topk: selected index k out of range (k=%d, size=%d)", k, cols);
   if (rows <= 0) return 0;
+  ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(rows) * cols * 4);
   topk_rows_kernel<<<rows, 256, 0, stream>>>(x, cols, k, out_v, out_i);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -387,6 +391,7 @@ int build_pair_items(const int64_t* top_ids, int num_pairs, int topn, const int*
                      KnnItem* items_q2o, KnnItem* items_o2q, cudaStream_t stream) {
   if (num_pairs <= 0) return 0;
   const int total = num_pairs * ((max_q + 127) / 128 + (max_p + 127) / 128);
+  ProfScope prof(PROF_RETRIEVAL, stream, total * 32.0);
   build_pair_items_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
       top_ids, num_pairs, topn, tpl_off, q_start, q_count, max_q, max_p, items_q2o, items_o2q);
   FP_CUDA_CHECK(cudaGetLastError());
@@ -405,6 +410,7 @@ int cyclic_buddies(const float* points, const int* q_start, const int* q_count, 
   if (num_pairs <= 0) return 0;
   int npow = 1;
   while (npow < max_q) npow <<= 1;
+  ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(num_pairs) * (max_q + max_p) * 8);
   cyclic_buddies_kernel<<<num_pairs, 512, npow * 8, stream>>>(
       points, q_start, q_count, q2o, o2q, top_ids, topn, tpl_off, feat_perm, vertices, max_q, max_p,
       top_k, out_qids, out_vids, out_dists, out_scores, out_c2d, out_c3d, out_count);

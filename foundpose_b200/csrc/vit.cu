@@ -168,6 +168,7 @@ int fp_vit_forward(fp_vit* handle, const float* images, int batch, int layer, in
                                  static_cast<size_t>(h->max_batch) * h->ntok * D * 4));
       }
       const int which = facet - 1;  // 1 = query, 2 = key, 3 = value
+      fp::ProfScope prof(fp::PROF_VIT_MISC, stream, static_cast<double>(M) * D * 6);
       fp::facet_gather_kernel<<<fp::kNumSMs * 4, 256, 0, stream>>>(h->qkv, h->facet_x, M, D, heads, which);
       FP_CUDA_CHECK(cudaGetLastError());
       final_src = h->facet_x;

@@ -192,6 +192,7 @@ int patchify_normalize(const float* img, __half* out, int B, int H, int W, int p
   FP_REQUIRE(W % ps == 0, "Input image width %d is not a multiple of patch width: %d", W, ps);
   FP_REQUIRE(Kpad >= 3 * ps * ps, "patchify: Kpad too small");
   const long total = static_cast<long>(B) * (H / ps) * (W / ps) * 3 * ps;
+  ProfScope prof(PROF_VIT_MISC, stream, static_cast<double>(B) * 3 * H * W * 4 + static_cast<double>(B) * (H / ps) * (W / ps) * Kpad * 2);
   patchify_normalize_kernel<<<grid_for(total, 256), 256, 0, stream>>>(img, out, B, H, W, ps, Kpad);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -200,6 +201,7 @@ int patchify_normalize(const float* img, __half* out, int B, int H, int W, int p
 int init_special_tokens(float* x, const float* cls_pos, const float* reg, int B, int ntok, int R,
                         int D, cudaStream_t stream) {
   const long total = static_cast<long>(B) * (1 + R) * D;
+  ProfScope prof(PROF_VIT_MISC, stream, static_cast<double>(total) * 4);
   init_special_tokens_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, cls_pos, reg, B, ntok, R, D);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -208,6 +210,7 @@ int init_special_tokens(float* x, const float* cls_pos, const float* reg, int B,
 int layernorm_f16(const float* x, __half* y, const float* w, const float* b, int M, int D, float eps,
                   cudaStream_t stream) {
   FP_REQUIRE(D % 128 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 128 and <= 2048", D);
+  ProfScope prof(PROF_LAYERNORM, stream, static_cast<double>(M) * D * 6);
   layernorm_f16_kernel<<<grid_for(M, 8), 256, 0, stream>>>(x, y, w, b, M, D, eps);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -218,6 +221,7 @@ int final_norm_tokens(const float* x, const float* w, const float* b, float* out
                       int apply_norm, float eps, cudaStream_t stream) {
   FP_REQUIRE(D % 128 == 0 && D <= 2048, "final_norm: D=%d must be a multiple of 128 and <= 2048", D);
   const long total = static_cast<long>(B) * (P + 1);
+  ProfScope prof(PROF_LAYERNORM, stream, static_cast<double>(total) * D * (out_tok16 ? 10 : 8));
   final_norm_tokens_kernel<<<grid_for(total, 8), 256, 0, stream>>>(x, w, b, out_tok, out_tok16,
                                                                   out_cls, B, ntok, R, P, D,
                                                                   apply_norm, eps);

@@ -203,6 +203,18 @@ int fp_cyclic_buddies(const float* points, const int32_t* q_start, const int32_t
                       int64_t* out_vertex_ids, float* out_dists, float* out_scores,
                       float* out_coord_2d, float* out_coord_3d, int32_t* out_count, void* stream);
 
+/* ---- launch accounting and per-kernel timing (used by bench.py) ---------------------------- */
+/* Number of kernels this library has launched since it was loaded (all threads). */
+unsigned long long fp_launch_count(void);
+/* Same, for one kernel family: 0 gemm, 1 attention, 2 layernorm, 3 vit misc, 4 knn,
+ * 5 feature ops, 6 retrieval. */
+unsigned long long fp_launch_count_category(int category);
+/* When on, every launch is bracketed by CUDA events on its stream. */
+int fp_profile_enable(int on);
+/* Sums device time (ms), algorithmic work (flops or bytes, see csrc/common.cuh) and launches
+ * recorded for a family since the last reset; synchronises on the recorded events. */
+int fp_profile_read(int category, double* total_ms, double* total_work, int* launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif
