@@ -50,6 +50,8 @@ def load() -> ctypes.CDLL:
     lib.fp_last_error.restype = ctypes.c_char_p
     lib.fp_last_error.argtypes = []
     lib.fp_version.restype = ctypes.c_int
+    lib.fp_launch_count.restype = ctypes.c_ulonglong
+    lib.fp_launch_count_category.restype = ctypes.c_ulonglong
     _lib = lib
     return lib
 

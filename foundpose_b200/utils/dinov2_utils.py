@@ -121,36 +121,43 @@ def _load_pretrained_state_dict(model_base_name: str, arch: synthetic.VitArch) -
         ) from e
 
 
+def parse_model_name(model_name: str) -> Dict[str, tp.Any]:
+    """Name grammar of the reference (utils/dinov2_utils.py:52-78): defaults + the two formats."""
+    opts: Dict[str, tp.Any] = {"version": "vits14-reg", "stride": 14, "facet": "token", "layer": 9, "norm": True}
+    name_items = model_name.split("_")
+    assert name_items[0] == "dinov2"
+    if len(name_items) == 2:
+        # Example: "dinov2_vits14"
+        opts["version"] = name_items[1]
+    else:
+        # Example: "dinov2_version=vitl14_stride=14_facet=key_layer=18_norm=1"
+        for item in name_items[1:]:
+            name, value = item.split("=")
+            if name == "version":
+                opts["version"] = value
+            elif name == "stride":
+                opts["stride"] = int(value)
+            elif name == "facet":
+                opts["facet"] = value
+            elif name == "layer":
+                opts["layer"] = int(value)
+            elif name == "norm":
+                opts["norm"] = bool(int(value))
+    return opts
+
+
 class DinoFeatureExtractor(nn.Module):
     """DINOv2 feature extractor (B200-native)."""
 
     def __init__(self, model_name: str, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  max_batch: int = 64) -> None:
         super().__init__()
-        # Default parameter values (reference dinov2_utils.py:52-57).
-        self.version: str = "vits14-reg"
-        self.stride: int = 14
-        self.facet: str = "token"
-        self.layer: int = 9
-        self.apply_norm: bool = True
-
-        name_items = model_name.split("_")
-        assert name_items[0] == "dinov2"
-        if len(name_items) == 2:
-            self.version = name_items[1]
-        else:
-            for item in name_items[1:]:
-                name, value = item.split("=")
-                if name == "version":
-                    self.version = value
-                elif name == "stride":
-                    self.stride = int(value)
-                elif name == "facet":
-                    self.facet = value
-                elif name == "layer":
-                    self.layer = int(value)
-                elif name == "norm":
-                    self.apply_norm = bool(int(value))
+        opts = parse_model_name(model_name)
+        self.version: str = opts["version"]
+        self.stride: int = opts["stride"]
+        self.facet: str = opts["facet"]
+        self.layer: int = opts["layer"]
+        self.apply_norm: bool = opts["norm"]
 
         if self.version not in synthetic.VIT_ARCHS:
             raise KeyError(f"Unknown DINOv2 version '{self.version}' (ViT-g / SwiGLU is not on the FoundPose path).")
