@@ -6,18 +6,22 @@
 //               the qkv GEMM epilogue writes (no head split / transpose pass)
 // Output: out  fp16 [B*N, D]    (column h*64 + d) - the operand layout of the proj GEMM
 //
-// One CTA = (128-query tile, head, image).  256 threads:
-//   warp 0      TMA producer: Q tile once, then K_j / V_j tiles (128 keys x 64) through rings
-//   warp 1      MMA issuer:   S_j = Q K_j^T      (M128 N128 K64, both operands K-major)
-//                             PV_j = P_j V_j     (M128 N64 K128, V used MN-major straight from
-//                                                 its natural [key, d] layout)
-//   warp 2      TMEM allocator (512 columns: S x2, PV x2)
-//   warps 4-7   softmax: one thread per query row; S_j from TMEM -> online softmax in fp32 ->
-//               P_j (fp16) into 128B-swizzled smem as the A operand of the PV MMA; the output
-//               accumulator O lives in registers and is rescaled there (O = O*alpha + PV_j), so
-//               no TMEM read-modify-write / correction pass is needed.
-// S and PV are double-buffered in TMEM, P in smem: the tensor core computes S_{j+1} while the
-// softmax warps work on S_j.
+// Persistent CTAs (one per SM, 384 threads) loop over work items = (pair of 128-query tiles, head,
+// image).  Warp roles:
+//   warp 0       TMA producer: the two Q tiles of the item, then K_j / V_j tiles (128 keys x 64)
+//                through 3-stage rings shared by both query tiles
+//   warp 1       MMA issuer:   S_X(j) = Q_X K_j^T   (M128 N<=128 K64, operands K-major)
+//                              PV_X(j) = P_X(j) V_j (M128 N64 K<=128, V MN-major from its natural
+//                                                    [key, d] layout)
+//                              L_X(j)  = P_X(j) 1   (M128 N16: exact fp32 row sums of the fp16 P)
+//   warp 2       TMEM allocator (512 columns: S_A, S_B, PV_A, PV_B, L_A, L_B)
+//   warps 4-7    softmax warpgroup of query tile A, warps 8-11 of tile B: one thread per query row.
+//                S(j) TMEM -> registers, running max in fp32, P = exp2 in packed f16x2 (one MUFU op
+//                per two probabilities) written to 128B-swizzled smem as the A operand of the next
+//                MMAs; O lives in registers and is rescaled there (O = O*alpha + PV(j)), so there
+//                is no TMEM read-modify-write / correction pass.
+// The two warpgroups ping-pong on the tensor core: while one computes its softmax the MMAs of the
+// other are in flight.  The last key block is only round_up(valid, 16) keys wide.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,24 +30,40 @@ namespace fp {
 namespace {
 
 constexpr int kHD = 64;        // head dim (all DINOv2 variants)
-constexpr int kBQ = 128;       // queries per CTA
+constexpr int kBQ = 128;       // queries per tile (two tiles per work item)
 constexpr int kBKV = 128;      // keys per block
 constexpr int kKVStages = 3;
-constexpr int kAttnThreads = 256;
+constexpr int kAttnThreads = 384;
 
-constexpr uint32_t kQBytes = kBQ * kHD * 2;      // 16 KB
+constexpr uint32_t kQBytes = kBQ * kHD * 2;      // 16 KB per query tile
 constexpr uint32_t kKBytes = kBKV * kHD * 2;     // 16 KB
 constexpr uint32_t kVBytes = kBKV * kHD * 2;     // 16 KB
 constexpr uint32_t kPBytes = kBQ * kBKV * 2;     // 32 KB (two 64-key swizzle atoms)
+constexpr uint32_t kOnesBytes = 4096;            // 16 x 128 fp16 ones (B operand of the row-sum MMA)
 
 struct AttnSmem {
   static constexpr uint32_t q_off = 0;
-  static constexpr uint32_t k_off = q_off + kQBytes;
+  static constexpr uint32_t k_off = q_off + 2 * kQBytes;
   static constexpr uint32_t v_off = k_off + kKVStages * kKBytes;
   static constexpr uint32_t p_off = v_off + kKVStages * kVBytes;
-  static constexpr uint32_t bar_off = p_off + 2 * kPBytes;
+  static constexpr uint32_t ones_off = p_off + 2 * kPBytes;
+  static constexpr uint32_t bar_off = ones_off + kOnesBytes;
   static constexpr uint32_t total = bar_off + 256 + 1024;
 };
+
+// TMEM column map (512 allocated)
+constexpr uint32_t kColS = 0;      // S_A at 0, S_B at 128
+constexpr uint32_t kColPV = 256;   // PV_A at 256, PV_B at 320
+constexpr uint32_t kColL = 384;    // L_A at 384, L_B at 400
+
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -51,9 +71,47 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Two probabilities per MUFU op: pack (lo, hi) to f16x2, exp2 on the packed pair.
+__device__ __forceinline__ uint32_t exp2_f16x2(float lo, float hi) {
+  uint32_t h, p;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(p) : "r"(h));
+  return p;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+
+// O = O * alpha + PV (64 columns, read from TMEM in 16-column pieces to bound register use),
+// l = l * alpha + rowsum(P).
+__device__ __forceinline__ void fold_pv(uint32_t tPV, uint32_t tL, float alpha, float (&o)[kHD],
+                                        float& l_run) {
+  uint32_t lsum;
+  tmem_ld_32x32b_x1(tL, lsum);
+#pragma unroll
+  for (int c = 0; c < kHD / 16; ++c) {
+    uint32_t t[16];
+    tmem_ld_32x32b_x16(tPV + c * 16, t);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[c * 16 + i] = fmaf(o[c * 16 + i], alpha, __uint_as_float(t[i]));
+  }
+  l_run = fmaf(l_run, alpha, __uint_as_float(lsum));
+  tc_fence_before_sync();
+}
+
+struct AttnBars {
+  uint64_t q_full, q_empty;
+  uint64_t k_full[kKVStages], k_empty[kKVStages];
+  uint64_t v_full[kKVStages], v_empty[kKVStages];
+  uint64_t s_full[2], s_empty[2], p_full[2], pv_done[2];
+  uint32_t tmem_slot;
+};
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int N, int D,
-                 float scale_log2e) {
+                 int heads, int num_items, float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -61,244 +119,255 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
   uint8_t* sK = smem + AttnSmem::k_off;
   uint8_t* sV = smem + AttnSmem::v_off;
   uint8_t* sP = smem + AttnSmem::p_off;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::bar_off);
-  uint64_t* q_full = bars;                    // 1
-  uint64_t* k_full = bars + 1;                // kKVStages
-  uint64_t* k_empty = k_full + kKVStages;     // kKVStages
-  uint64_t* v_full = k_empty + kKVStages;     // kKVStages
-  uint64_t* v_empty = v_full + kKVStages;     // kKVStages
-  uint64_t* s_full = v_empty + kKVStages;     // 2
-  uint64_t* s_empty = s_full + 2;             // 2
-  uint64_t* p_full = s_empty + 2;             // 2
-  uint64_t* pv_done = p_full + 2;             // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint8_t* sOnes = smem + AttnSmem::ones_off;
+  AttnBars* bars = reinterpret_cast<AttnBars*>(smem + AttnSmem::bar_off);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x;
-  const int head = blockIdx.y;
-  const int img = blockIdx.z;
-  const int q0 = q_tile * kBQ;
-  const int row_base = img * N;            // first token row of this image in the qkv matrix
   const int num_kv = (N + kBKV - 1) / kBKV;
+  const int pairs = (N + 2 * kBQ - 1) / (2 * kBQ);
+  // Width of the last key block: only as many 16-key MMA steps as there are valid keys.
+  const int last_valid = N - (num_kv - 1) * kBKV;
+  const int last_len = (last_valid + 15) / 16 * 16;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
-    mbar_init(q_full, 1);
+    mbar_init(&bars->q_full, 1);
+    mbar_init(&bars->q_empty, 1);
     for (int s = 0; s < kKVStages; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&bars->k_full[s], 1);
+      mbar_init(&bars->k_empty[s], 1);
+      mbar_init(&bars->v_full[s], 1);
+      mbar_init(&bars->v_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 4);   // one arrive per softmax warp
-      mbar_init(&p_full[b], 4);
-      mbar_init(&pv_done[b], 1);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&bars->s_full[x], 1);
+      mbar_init(&bars->s_empty[x], 4);   // one arrive per softmax warp of that tile
+      mbar_init(&bars->p_full[x], 4);
+      mbar_init(&bars->pv_done[x], 1);
     }
     fence_barrier_init();
   } else if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(&bars->tmem_slot, 512);
     tmem_relinquish();
+  } else if (warp == 3) {
+    // fp16 1.0 everywhere: any descriptor pointing into this region reads a ones matrix.
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(sOnes);
+    for (int i = lane; i < static_cast<int>(kOnesBytes / 4); i += 32) o32[i] = 0x3C003C00u;
+    fence_proxy_async_smem();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;          // 2 x 128 columns
-  const uint32_t tmem_PV = tmem_base + 256;   // 2 x 64 columns
+  const uint32_t tmem_base = bars->tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_2d(sQ, &tmQKV, q_full, head * kHD, row_base + q0);
+  if (warp < 4) {
+    reg_dealloc<72>();
+    if (warp == 0 && lane == 0) {
+      // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < num_kv; ++j) {
-        mbar_wait(&k_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&k_full[stage], kKBytes);
-        tma_load_2d(sK + stage * kKBytes, &tmQKV, &k_full[stage], D + head * kHD,
-                    row_base + j * kBKV);
-        mbar_wait(&v_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&v_full[stage], kVBytes);
-        tma_load_2d(sV + stage * kVBytes, &tmQKV, &v_full[stage], 2 * D + head * kHD,
-                    row_base + j * kBKV);
-        if (++stage == kKVStages) { stage = 0; phase ^= 1; }
+      uint32_t item_phase = 0;
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+        const int pair = it % pairs;
+        const int head = (it / pairs) % heads;
+        const int img = it / (pairs * heads);
+        const int row_base = img * N;
+        mbar_wait(&bars->q_empty, item_phase ^ 1);
+        mbar_arrive_expect_tx(&bars->q_full, 2 * kQBytes);
+        tma_load_2d(sQ, &tmQKV, &bars->q_full, head * kHD, row_base + pair * 2 * kBQ);
+        tma_load_2d(sQ + kQBytes, &tmQKV, &bars->q_full, head * kHD, row_base + pair * 2 * kBQ + kBQ);
+        item_phase ^= 1;
+        for (int j = 0; j < num_kv; ++j) {
+          mbar_wait(&bars->k_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bars->k_full[stage], kKBytes);
+          tma_load_2d(sK + stage * kKBytes, &tmQKV, &bars->k_full[stage], D + head * kHD,
+                      row_base + j * kBKV);
+          mbar_wait(&bars->v_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bars->v_full[stage], kVBytes);
+          tma_load_2d(sV + stage * kVBytes, &tmQKV, &bars->v_full[stage], 2 * D + head * kHD,
+                      row_base + j * kBKV);
+          if (++stage == kKVStages) { stage = 0; phase ^= 1; }
+        }
       }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_f16(kBQ, kHD, 0, 1);  // B (=V) is MN-major
-      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
-      mbar_wait(q_full, 0);
-      tc_fence_after_sync();
+    } else if (warp == 1 && lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_pv = make_idesc_f16(kBQ, kHD, 0, 1);   // B (=V) is MN-major
+      constexpr uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0);
+      const uint64_t qdesc[2] = {make_smem_desc_sw128(smem_u32(sQ)),
+                                 make_smem_desc_sw128(smem_u32(sQ + kQBytes))};
+      const uint32_t ones_addr = smem_u32(sOnes);
       int kstage = 0, vstage = 0;
-      uint32_t kphase = 0, vphase = 0;
-      // Software pipeline: S_j is issued before PV_{j-1} so the softmax of block j can start
-      // while the tensor core still works on PV_{j-1}.
-      for (int j = 0; j <= num_kv; ++j) {
-        if (j < num_kv) {
-          const int b = j & 1;
-          const uint32_t use = static_cast<uint32_t>(j >> 1);  // how often buffer b was used before
-          mbar_wait(&k_full[kstage], kphase);
-          mbar_wait(&s_empty[b], (use & 1) ^ 1);
-          tc_fence_after_sync();
-          const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + kstage * kKBytes));
+      uint32_t kphase = 0, vphase = 0, item_phase = 0;
+      uint32_t blk = 0;   // running count of key blocks processed by this CTA (barrier parity)
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+        mbar_wait(&bars->q_full, item_phase);
+        item_phase ^= 1;
+        tc_fence_after_sync();
+        for (int j = 0; j <= num_kv; ++j) {
+          if (j < num_kv) {
+            const int len = (j == num_kv - 1) ? last_len : kBKV;
+            const uint32_t idesc_s = make_idesc_f16(kBQ, len, 0, 0);
+            const uint32_t par = (blk + j) & 1;
+            mbar_wait(&bars->k_full[kstage], kphase);
+            const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + kstage * kKBytes));
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k)
-            umma_f16_ss(tmem_S + b * kBKV, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(&k_empty[kstage]);
-          umma_commit(&s_full[b]);
-          if (++kstage == kKVStages) { kstage = 0; kphase ^= 1; }
-        }
-        if (j >= 1) {
-          const int jj = j - 1;
-          const int b = jj & 1;
-          const uint32_t use = static_cast<uint32_t>(jj >> 1);
-          mbar_wait(&v_full[vstage], vphase);
-          mbar_wait(&p_full[b], use & 1);
-          tc_fence_after_sync();
-          const uint32_t p_addr = smem_u32(sP + b * kPBytes);
-          const uint32_t v_addr = smem_u32(sV + vstage * kVBytes);
+            for (int x = 0; x < 2; ++x) {
+              mbar_wait(&bars->s_empty[x], par ^ 1);
+              tc_fence_after_sync();
 #pragma unroll
-          for (int k = 0; k < kBKV / 16; ++k) {
-            // A = P: K-major, two 64-key atoms of 16 KB; +32 B per 16 keys inside an atom.
-            const uint64_t pdesc =
-                make_smem_desc_sw128(p_addr + (k >> 2) * (kBQ * 128) + (k & 3) * 32);
-            // B = V: MN-major, 16 key rows of 128 B per K step.
-            const uint64_t vdesc = make_smem_desc_sw128(v_addr + k * 2048);
-            umma_f16_ss(tmem_PV + b * kHD, pdesc, vdesc, idesc_pv, k != 0);
+              for (int k = 0; k < kHD / 16; ++k)
+                umma_f16_ss(tmem_base + kColS + x * kBKV, qdesc[x] + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+              umma_commit(&bars->s_full[x]);
+            }
+            umma_commit(&bars->k_empty[kstage]);
+            if (j == num_kv - 1) umma_commit(&bars->q_empty);   // Q tiles may be overwritten
+            if (++kstage == kKVStages) { kstage = 0; kphase ^= 1; }
           }
-          umma_commit(&v_empty[vstage]);
-          umma_commit(&pv_done[b]);
-          if (++vstage == kKVStages) { vstage = 0; vphase ^= 1; }
+          if (j >= 1) {
+            const int jj = j - 1;
+            const int len = (jj == num_kv - 1) ? last_len : kBKV;
+            const uint32_t par = (blk + jj) & 1;
+            mbar_wait(&bars->v_full[vstage], vphase);
+            const uint32_t v_addr = smem_u32(sV + vstage * kVBytes);
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              mbar_wait(&bars->p_full[x], par);
+              tc_fence_after_sync();
+              const uint32_t p_addr = smem_u32(sP + x * kPBytes);
+              for (int k = 0; k < len / 16; ++k) {
+                // A = P: K-major, two 64-key atoms of 16 KB; +32 B per 16 keys inside an atom.
+                const uint64_t pdesc =
+                    make_smem_desc_sw128(p_addr + (k >> 2) * (kBQ * 128) + (k & 3) * 32);
+                // B = V: MN-major, 16 key rows of 128 B per K step.
+                const uint64_t vdesc = make_smem_desc_sw128(v_addr + k * 2048);
+                umma_f16_ss(tmem_base + kColPV + x * kHD, pdesc, vdesc, idesc_pv, k != 0);
+                // Row sums of P: B = ones (16 x 16 keys per step).
+                const uint64_t odesc = make_smem_desc_sw128(ones_addr + (k & 3) * 32);
+                umma_f16_ss(tmem_base + kColL + x * 16, pdesc, odesc, idesc_l, k != 0);
+              }
+              umma_commit(&bars->pv_done[x]);
+            }
+            umma_commit(&bars->v_empty[vstage]);
+            if (++vstage == kKVStages) { vstage = 0; vphase ^= 1; }
+          }
         }
+        blk += num_kv;
       }
     }
-    __syncwarp();
-  } else if (warp >= 4) {
+  } else {
+    // ===== softmax warpgroups =====
+    reg_alloc<216>();
+    const int x = (warp - 4) >> 2;                      // query tile of this warpgroup (0 = A, 1 = B)
     const int sub = warp & 3;
     const int r = sub * 32 + lane;                      // query row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
-    float o[kHD];
+    const uint32_t tS = tmem_base + lane_addr + kColS + x * kBKV;
+    const uint32_t tPV = tmem_base + lane_addr + kColPV + x * kHD;
+    const uint32_t tL = tmem_base + lane_addr + kColL + x * 16;
+    uint8_t* prow = sP + x * kPBytes + r * 128;
+    uint32_t blk = 0;
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      const int pair = it % pairs;
+      const int head = (it / pairs) % heads;
+      const int img = it / (pairs * heads);
+      const int row_base = img * N;
+      float o[kHD];
 #pragma unroll
-    for (int i = 0; i < kHD; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+      for (int i = 0; i < kHD; ++i) o[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
 
-    for (int j = 0; j <= num_kv; ++j) {
-      if (j < num_kv) {
-        const int b = j & 1;
-        const uint32_t use = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&s_full[b], use & 1);
-        tc_fence_after_sync();
-        uint32_t s[kBKV];
+      for (int j = 0; j <= num_kv; ++j) {
+        if (j < num_kv) {
+          const uint32_t par = (blk + j) & 1;
+          const int valid = N - j * kBKV;            // keys >= valid are out of range
+          const int len = (j == num_kv - 1) ? last_len : kBKV;
+          mbar_wait(&bars->s_full[x], par);
+          tc_fence_after_sync();
+          uint32_t s[kBKV];
 #pragma unroll
-        for (int c = 0; c < kBKV / 32; ++c) {
-          uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
-          tmem_ld_32x32b_x32(tmem_S + lane_addr + b * kBKV + c * 32, chunk);
-        }
-        tmem_ld_wait();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[b]);
-
-        const int valid = N - j * kBKV;  // keys >= valid are out of range in this block
-        float m_blk = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < kBKV; ++i) {
-          float v = __uint_as_float(s[i]);
-          if (i >= valid) v = -INFINITY;
-          s[i] = __float_as_uint(v);
-          m_blk = fmaxf(m_blk, v);
-        }
-        const float m_new = fmaxf(m_run, m_blk);
-        const float alpha = fast_exp2((m_run - m_new) * scale_log2e);  // 0 on the first block
-        const float neg_m = -m_new * scale_log2e;
-        float l_blk = 0.f;
-        // P buffer b was last read by PV_{j-2}: that MMA has retired (we waited on pv_done for
-        // it when consuming PV_{j-2} at iteration j-1).
-        uint8_t* prow = sP + b * kPBytes + r * 128;
-#pragma unroll
-        for (int c = 0; c < kBKV / 8; ++c) {
-          float p[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            p[i] = fast_exp2(fmaf(__uint_as_float(s[c * 8 + i]), scale_log2e, neg_m));
-            l_blk += p[i];
+          for (int c = 0; c < kBKV / 32; ++c) {
+            if (c * 32 < len) {
+              uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
+              tmem_ld_32x32b_x32(tS + c * 32, chunk);
+            }
           }
-          __half2 h0 = __floats2half2_rn(p[0], p[1]);
-          __half2 h1 = __floats2half2_rn(p[2], p[3]);
-          __half2 h2 = __floats2half2_rn(p[4], p[5]);
-          __half2 h3 = __floats2half2_rn(p[6], p[7]);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->s_empty[x]);   // S may be recomputed for the next block
+
+          float m_blk = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < kBKV; ++i) {
+            if (i < len) {
+              float v = __uint_as_float(s[i]);
+              if (i >= valid) v = -INFINITY;
+              s[i] = __float_as_uint(v);
+              m_blk = fmaxf(m_blk, v);
+            }
+          }
+          const float m_new = fmaxf(m_run, m_blk);
+          const float alpha = fast_exp2((m_run - m_new) * scale_log2e);  // 0 on the first block
+          const float neg_m = -m_new * scale_log2e;
+
+          // The P buffer of this tile was last read by PV(j-1): wait for it, then fold PV(j-1)
+          // (relative to m_{j-1}) into O; alpha_prev rescales O from m_{j-2} to m_{j-1}.
+          if (j >= 1) {
+            mbar_wait(&bars->pv_done[x], par ^ 1);
+            tc_fence_after_sync();
+            fold_pv(tPV, tL, alpha_prev, o, l_run);
+          }
+
+#pragma unroll
+          for (int c = 0; c < kBKV / 8; ++c) {
+            if (c * 8 < len) {
+              uint4 pk;
+              pk.x = exp2_f16x2(fmaf(__uint_as_float(s[c * 8 + 0]), scale_log2e, neg_m),
+                                fmaf(__uint_as_float(s[c * 8 + 1]), scale_log2e, neg_m));
+              pk.y = exp2_f16x2(fmaf(__uint_as_float(s[c * 8 + 2]), scale_log2e, neg_m),
+                                fmaf(__uint_as_float(s[c * 8 + 3]), scale_log2e, neg_m));
+              pk.z = exp2_f16x2(fmaf(__uint_as_float(s[c * 8 + 4]), scale_log2e, neg_m),
+                                fmaf(__uint_as_float(s[c * 8 + 5]), scale_log2e, neg_m));
+              pk.w = exp2_f16x2(fmaf(__uint_as_float(s[c * 8 + 6]), scale_log2e, neg_m),
+                                fmaf(__uint_as_float(s[c * 8 + 7]), scale_log2e, neg_m));
+              // 128B swizzle: 16-byte chunk index XOR (row % 8); atom = c / 8.
+              const int atom = c >> 3, cc = c & 7;
+              *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
+            }
+          }
+          m_run = m_new;
+          fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the UMMA
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->p_full[x]);
+          alpha_prev = alpha;
+        } else {
+          // Drain: PV and row sums of the last block.
+          const uint32_t par = (blk + j - 1) & 1;
+          mbar_wait(&bars->pv_done[x], par);
+          tc_fence_after_sync();
+          fold_pv(tPV, tL, alpha_prev, o, l_run);
+        }
+      }
+      blk += num_kv;
+
+      const int q = pair * 2 * kBQ + x * kBQ + r;
+      if (q < N) {
+        const float inv_l = 1.0f / l_run;
+        __half* dst = out + static_cast<size_t>(row_base + q) * D + head * kHD;
+#pragma unroll
+        for (int c = 0; c < kHD / 8; ++c) {
+          __half2 h0 = __floats2half2_rn(o[c * 8 + 0] * inv_l, o[c * 8 + 1] * inv_l);
+          __half2 h1 = __floats2half2_rn(o[c * 8 + 2] * inv_l, o[c * 8 + 3] * inv_l);
+          __half2 h2 = __floats2half2_rn(o[c * 8 + 4] * inv_l, o[c * 8 + 5] * inv_l);
+          __half2 h3 = __floats2half2_rn(o[c * 8 + 6] * inv_l, o[c * 8 + 7] * inv_l);
           uint4 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&h0);
           pk.y = *reinterpret_cast<uint32_t*>(&h1);
           pk.z = *reinterpret_cast<uint32_t*>(&h2);
           pk.w = *reinterpret_cast<uint32_t*>(&h3);
-          // 128B swizzle: 16-byte chunk index XOR (row % 8); atom = c / 8.
-          const int atom = c >> 3, cc = c & 7;
-          *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(dst + c * 8) = pk;
         }
-        l_run = l_run * alpha + l_blk;
-        m_run = m_new;
-        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the UMMA (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[b]);
-
-        // Consume PV_{j-1} (relative to m_{j-1}); alpha_prev rescales O from m_{j-2} to m_{j-1}.
-        if (j >= 1) {
-          const int pb = (j - 1) & 1;
-          const uint32_t puse = static_cast<uint32_t>((j - 1) >> 1);
-          mbar_wait(&pv_done[pb], puse & 1);
-          tc_fence_after_sync();
-          uint32_t t[kHD];
-          uint32_t(&t0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&t[0]);
-          uint32_t(&t1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&t[32]);
-          tmem_ld_32x32b_x32(tmem_PV + lane_addr + pb * kHD, t0);
-          tmem_ld_32x32b_x32(tmem_PV + lane_addr + pb * kHD + 32, t1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < kHD; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(t[i]));
-          tc_fence_before_sync();
-        }
-        alpha_prev = alpha;
-      } else {
-        // Drain: PV of the last block.
-        const int pb = (j - 1) & 1;
-        const uint32_t puse = static_cast<uint32_t>((j - 1) >> 1);
-        mbar_wait(&pv_done[pb], puse & 1);
-        tc_fence_after_sync();
-        uint32_t t[kHD];
-        uint32_t(&t0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&t[0]);
-        uint32_t(&t1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&t[32]);
-        tmem_ld_32x32b_x32(tmem_PV + lane_addr + pb * kHD, t0);
-        tmem_ld_32x32b_x32(tmem_PV + lane_addr + pb * kHD + 32, t1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < kHD; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(t[i]));
-        tc_fence_before_sync();
-      }
-    }
-
-    const int q = q0 + r;
-    if (q < N) {
-      const float inv_l = 1.0f / l_run;
-      __half* dst = out + static_cast<size_t>(row_base + q) * D + head * kHD;
-#pragma unroll
-      for (int c = 0; c < kHD / 8; ++c) {
-        __half2 h0 = __floats2half2_rn(o[c * 8 + 0] * inv_l, o[c * 8 + 1] * inv_l);
-        __half2 h1 = __floats2half2_rn(o[c * 8 + 2] * inv_l, o[c * 8 + 3] * inv_l);
-        __half2 h2 = __floats2half2_rn(o[c * 8 + 4] * inv_l, o[c * 8 + 5] * inv_l);
-        __half2 h3 = __floats2half2_rn(o[c * 8 + 6] * inv_l, o[c * 8 + 7] * inv_l);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        pk.z = *reinterpret_cast<uint32_t*>(&h2);
-        pk.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(dst + c * 8) = pk;
       }
     }
   }
@@ -325,10 +394,13 @@ int attention_f16(const __half* qkv, __half* out, int B, int N, int heads, cudaS
                                        AttnSmem::total));
     configured = true;
   }
-  dim3 grid((N + kBQ - 1) / kBQ, heads, B);
+  const int pairs = (N + 2 * kBQ - 1) / (2 * kBQ);
+  const int num_items = pairs * heads * B;
+  const int grid = num_items < kNumSMs ? num_items : kNumSMs;
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // hd^-0.5 * log2(e), hd = 64
   ProfScope prof(PROF_ATTENTION, stream, 4.0 * B * heads * static_cast<double>(N) * N * kHD);
-  attention_kernel<<<grid, kAttnThreads, AttnSmem::total, stream>>>(tm, out, N, D, scale_log2e);
+  attention_kernel<<<grid, kAttnThreads, AttnSmem::total, stream>>>(tm, out, N, D, heads, num_items,
+                                                                    scale_log2e);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
