@@ -83,22 +83,41 @@ __device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 
-// O = O * alpha + PV (64 columns, read from TMEM in 16-column pieces to bound register use),
-// l = l * alpha + rowsum(P).
-__device__ __forceinline__ void fold_pv(uint32_t tPV, uint32_t tL, float alpha, float (&o)[kHD],
-                                        float& l_run) {
-  uint32_t lsum;
-  tmem_ld_32x32b_x1(tL, lsum);
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
+        "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// O (64 columns) and the row sum L accumulate in TMEM across key blocks.  When the running max of
+// a row moves by more than 2^8 the accumulators are rescaled in place: O *= alpha, L *= alpha
+// (warp-collective TMEM load / multiply / store; rare after the first blocks).
+__device__ __forceinline__ void rescale_accumulators(uint32_t tPV, uint32_t tL, float alpha) {
 #pragma unroll
   for (int c = 0; c < kHD / 16; ++c) {
     uint32_t t[16];
     tmem_ld_32x32b_x16(tPV + c * 16, t);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[c * 16 + i] = fmaf(o[c * 16 + i], alpha, __uint_as_float(t[i]));
+    for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+    tmem_st_32x32b_x16(tPV + c * 16, t);
   }
-  l_run = fmaf(l_run, alpha, __uint_as_float(lsum));
-  tc_fence_before_sync();
+  uint32_t l;
+  tmem_ld_32x32b_x1(tL, l);
+  tmem_ld_wait();
+  tmem_st_32x32b_x1(tL, __float_as_uint(__uint_as_float(l) * alpha));
+  tmem_st_wait();
 }
 
 struct AttnBars {
@@ -108,6 +127,103 @@ struct AttnBars {
   uint64_t s_full[2], s_empty[2], p_full[2], pv_done[2];
   uint32_t tmem_slot;
 };
+
+// Online softmax of one key block for one query row (= one thread).  The reference max is updated
+// lazily: the TMEM accumulators are only rescaled when a row's max moved by more than 2^8, so
+// P <= 256 stays well inside fp16 and the rescale is rare after the first blocks.
+constexpr float kRescaleThreshold = 8.0f;   // log2 domain
+
+// Shared tail of both block variants: given the block max, decide whether the accumulators must be
+// rescaled (after PV(j-1) retired) and return -m_used * c.
+__device__ __forceinline__ float update_reference_max(AttnBars* bars, int x, uint32_t tPV, uint32_t tL,
+                                                      bool first, uint32_t par, float scale_log2e,
+                                                      float m_blk, float& m_used) {
+  const float m_new = fmaxf(m_used, m_blk);
+  if (first) {
+    m_used = m_new;
+  } else {
+    // PV(j-1) done: the P buffer may be overwritten and O / L are stable.
+    mbar_wait(&bars->pv_done[x], par ^ 1);
+    tc_fence_after_sync();
+    const bool need = (m_new - m_used) * scale_log2e > kRescaleThreshold;
+    if (__any_sync(0xffffffffu, need)) {
+      rescale_accumulators(tPV, tL, fast_exp2((m_used - m_new) * scale_log2e));
+      m_used = m_new;
+      tc_fence_before_sync();
+    }
+  }
+  return -m_used * scale_log2e;
+}
+
+__device__ __forceinline__ void store_p8(uint8_t* prow, int r, int c, const uint32_t* s8, float scale_log2e,
+                                         float neg_m) {
+  uint4 pk;
+  pk.x = exp2_f16x2(fmaf(__uint_as_float(s8[0]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[1]), scale_log2e, neg_m));
+  pk.y = exp2_f16x2(fmaf(__uint_as_float(s8[2]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[3]), scale_log2e, neg_m));
+  pk.z = exp2_f16x2(fmaf(__uint_as_float(s8[4]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[5]), scale_log2e, neg_m));
+  pk.w = exp2_f16x2(fmaf(__uint_as_float(s8[6]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[7]), scale_log2e, neg_m));
+  // 128B swizzle: 16-byte chunk index XOR (row % 8); atom = c / 8.
+  const int atom = c >> 3, cc = c & 7;
+  *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
+}
+
+// Full block: all 128 keys valid - fully static code, S held in registers (one TMEM pass).
+__device__ __forceinline__ void softmax_block_full(AttnBars* bars, int x, int lane, uint32_t tS, uint32_t tPV,
+                                                   uint32_t tL, uint8_t* prow, int r, bool first,
+                                                   uint32_t par, float scale_log2e, float& m_used) {
+  uint32_t s[kBKV];
+#pragma unroll
+  for (int c = 0; c < kBKV / 32; ++c) {
+    uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
+    tmem_ld_32x32b_x32(tS + c * 32, chunk);
+  }
+  tmem_ld_wait();
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&bars->s_empty[x]);   // S may be recomputed for the next block
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int i = 0; i < kBKV; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[i]));
+  const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+  const float neg_m = update_reference_max(bars, x, tPV, tL, first, par, scale_log2e, m_blk, m_used);
+#pragma unroll
+  for (int c = 0; c < kBKV / 8; ++c) store_p8(prow, r, c, &s[c * 8], scale_log2e, neg_m);
+}
+
+// Last (partial) block: `len` (multiple of 16) columns were computed, keys >= valid are masked.
+// Two TMEM passes over 32-column chunks keep the register footprint small; it runs once per item.
+__device__ __forceinline__ void softmax_block_tail(AttnBars* bars, int x, int lane, uint32_t tS, uint32_t tPV,
+                                                   uint32_t tL, uint8_t* prow, int r, int len, int valid,
+                                                   bool first, uint32_t par, float scale_log2e,
+                                                   float& m_used) {
+  const int chunks = (len + 31) / 32;
+  float m_blk = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < chunks; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tS + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c * 32 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+  }
+  const float neg_m = update_reference_max(bars, x, tPV, tL, first, par, scale_log2e, m_blk, m_used);
+#pragma unroll 1
+  for (int c = 0; c < chunks; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tS + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c * 32 + i >= valid) v[i] = 0xff800000u;   // -inf -> P = 0
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (c * 32 + g * 8 < len) store_p8(prow, r, c * 4 + g, &v[g * 8], scale_log2e, neg_m);
+  }
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&bars->s_empty[x]);
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int N, int D,
@@ -162,7 +278,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
   const uint32_t tmem_base = bars->tmem_slot;
 
   if (warp < 4) {
-    reg_dealloc<72>();
     if (warp == 0 && lane == 0) {
       // ===== TMA producer =====
       int stage = 0;
@@ -241,10 +356,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
                     make_smem_desc_sw128(p_addr + (k >> 2) * (kBQ * 128) + (k & 3) * 32);
                 // B = V: MN-major, 16 key rows of 128 B per K step.
                 const uint64_t vdesc = make_smem_desc_sw128(v_addr + k * 2048);
-                umma_f16_ss(tmem_base + kColPV + x * kHD, pdesc, vdesc, idesc_pv, k != 0);
+                umma_f16_ss(tmem_base + kColPV + x * kHD, pdesc, vdesc, idesc_pv, (jj | k) != 0);
                 // Row sums of P: B = ones (16 x 16 keys per step).
                 const uint64_t odesc = make_smem_desc_sw128(ones_addr + (k & 3) * 32);
-                umma_f16_ss(tmem_base + kColL + x * 16, pdesc, odesc, idesc_l, k != 0);
+                umma_f16_ss(tmem_base + kColL + x * 16, pdesc, odesc, idesc_l, (jj | k) != 0);
               }
               umma_commit(&bars->pv_done[x]);
             }
@@ -257,7 +372,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
     }
   } else {
     // ===== softmax warpgroups =====
-    reg_alloc<216>();
     const int x = (warp - 4) >> 2;                      // query tile of this warpgroup (0 = A, 1 = B)
     const int sub = warp & 3;
     const int r = sub * 32 + lane;                      // query row inside the tile
@@ -272,83 +386,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
       const int head = (it / pairs) % heads;
       const int img = it / (pairs * heads);
       const int row_base = img * N;
-      float o[kHD];
-#pragma unroll
-      for (int i = 0; i < kHD; ++i) o[i] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-
-      for (int j = 0; j <= num_kv; ++j) {
-        if (j < num_kv) {
-          const uint32_t par = (blk + j) & 1;
-          const int valid = N - j * kBKV;            // keys >= valid are out of range
-          const int len = (j == num_kv - 1) ? last_len : kBKV;
-          mbar_wait(&bars->s_full[x], par);
-          tc_fence_after_sync();
-          uint32_t s[kBKV];
-#pragma unroll
-          for (int c = 0; c < kBKV / 32; ++c) {
-            if (c * 32 < len) {
-              uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
-              tmem_ld_32x32b_x32(tS + c * 32, chunk);
-            }
-          }
-          tmem_ld_wait();
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->s_empty[x]);   // S may be recomputed for the next block
-
-          float m_blk = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < kBKV; ++i) {
-            if (i < len) {
-              float v = __uint_as_float(s[i]);
-              if (i >= valid) v = -INFINITY;
-              s[i] = __float_as_uint(v);
-              m_blk = fmaxf(m_blk, v);
-            }
-          }
-          const float m_new = fmaxf(m_run, m_blk);
-          const float alpha = fast_exp2((m_run - m_new) * scale_log2e);  // 0 on the first block
-          const float neg_m = -m_new * scale_log2e;
-
-          // The P buffer of this tile was last read by PV(j-1): wait for it, then fold PV(j-1)
-          // (relative to m_{j-1}) into O; alpha_prev rescales O from m_{j-2} to m_{j-1}.
-          if (j >= 1) {
-            mbar_wait(&bars->pv_done[x], par ^ 1);
-            tc_fence_after_sync();
-            fold_pv(tPV, tL, alpha_prev, o, l_run);
-          }
-
-#pragma unroll
-          for (int c = 0; c < kBKV / 8; ++c) {
-            if (c * 8 < len) {
-              uint4 pk;
-              pk.x = exp2_f16x2(fmaf(__uint_as_float(s[c * 8 + 0]), scale_log2e, neg_m),
-                                fmaf(__uint_as_float(s[c * 8 + 1]), scale_log2e, neg_m));
-              pk.y = exp2_f16x2(fmaf(__uint_as_float(s[c * 8 + 2]), scale_log2e, neg_m),
-                                fmaf(__uint_as_float(s[c * 8 + 3]), scale_log2e, neg_m));
-              pk.z = exp2_f16x2(fmaf(__uint_as_float(s[c * 8 + 4]), scale_log2e, neg_m),
-                                fmaf(__uint_as_float(s[c * 8 + 5]), scale_log2e, neg_m));
-              pk.w = exp2_f16x2(fmaf(__uint_as_float(s[c * 8 + 6]), scale_log2e, neg_m),
-                                fmaf(__uint_as_float(s[c * 8 + 7]), scale_log2e, neg_m));
-              // 128B swizzle: 16-byte chunk index XOR (row % 8); atom = c / 8.
-              const int atom = c >> 3, cc = c & 7;
-              *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
-            }
-          }
-          m_run = m_new;
-          fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the UMMA
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->p_full[x]);
-          alpha_prev = alpha;
+      float m_used = -INFINITY;
+      for (int j = 0; j < num_kv; ++j) {
+        const uint32_t par = (blk + j) & 1;
+        const int valid = N - j * kBKV;            // keys >= valid are out of range
+        const int len = (j == num_kv - 1) ? last_len : kBKV;
+        mbar_wait(&bars->s_full[x], par);
+        tc_fence_after_sync();
+        if (len == kBKV && valid >= kBKV) {
+          softmax_block_full(bars, x, lane, tS, tPV, tL, prow, r, j == 0, par, scale_log2e, m_used);
         } else {
-          // Drain: PV and row sums of the last block.
-          const uint32_t par = (blk + j - 1) & 1;
-          mbar_wait(&bars->pv_done[x], par);
-          tc_fence_after_sync();
-          fold_pv(tPV, tL, alpha_prev, o, l_run);
+          softmax_block_tail(bars, x, lane, tS, tPV, tL, prow, r, len, valid, j == 0, par, scale_log2e, m_used);
         }
+        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the UMMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_full[x]);
       }
+      // Drain: O and the row sums are complete once PV of the last block has retired.
+      mbar_wait(&bars->pv_done[x], (blk + num_kv - 1) & 1);
+      tc_fence_after_sync();
+      float o[kHD];
+      uint32_t lsum;
+      tmem_ld_32x32b_x1(tL, lsum);
+#pragma unroll
+      for (int c = 0; c < kHD / 16; ++c) {
+        uint32_t(&t)[16] = *reinterpret_cast<uint32_t(*)[16]>(&o[c * 16]);
+        tmem_ld_32x32b_x16(tPV + c * 16, t);
+      }
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      const float l_run = __uint_as_float(lsum);
       blk += num_kv;
 
       const int q = pair * 2 * kBQ + x * kBQ + r;
