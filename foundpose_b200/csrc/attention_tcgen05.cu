@@ -10,14 +10,13 @@
 // image).  Warp roles:
 //   warp 0       TMA producer: the two Q tiles of the item, then K_j / V_j tiles (128 keys x 64)
 //                through 3-stage rings shared by both query tiles
-//   warp 1       MMA issuer:   S_X(j) = Q_X K_j^T   (M128 N<=128 K64, operands K-major)
-//                              PV_X(j) = P_X(j) V_j (M128 N64 K<=128, V MN-major from its natural
+//   warp 1       MMA issuer 1: S_X(j) = Q_X K_j^T   (M128 N<=128 K64, operands K-major)
+//   warp 3       MMA issuer 2: PV_X(j) = P_X(j) V_j (M128 N64 K<=128, V MN-major from its natural
 //                                                    [key, d] layout)
 //                              L_X(j)  = P_X(j) 1   (M128 N16: exact fp32 row sums of the fp16 P)
 //   warp 2       TMEM allocator (512 columns: S_A, S_B, PV_A, PV_B, L_A, L_B)
 //   warps 4-7    softmax warpgroup of query tile A, warps 8-11 of tile B: one thread per query row.
-//                S(j) TMEM -> registers, running max in fp32, P = exp2 in packed f16x2 (one MUFU op
-//                per two probabilities) written to 128B-swizzled smem as the A operand of the next
+//                S(j) TMEM -> registers, running max in fp32, P = exp2(...) packed to f16x2 and written to 128B-swizzled smem as the A operand of the next
 //                MMAs; O lives in registers and is rescaled there (O = O*alpha + PV(j)), so there
 //                is no TMEM read-modify-write / correction pass.
 // The two warpgroups ping-pong on the tensor core: while one computes its softmax the MMAs of the
@@ -71,11 +70,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Two probabilities per MUFU op: pack (lo, hi) to f16x2, exp2 on the packed pair.
+// exp2 of two scores in fp32 (MUFU.EX2), packed to f16x2 for the P operand.
 __device__ __forceinline__ uint32_t exp2_f16x2(float lo, float hi) {
-  uint32_t h, p;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(p) : "r"(h));
+  uint32_t p;
+  const float elo = fast_exp2(lo), ehi = fast_exp2(hi);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(ehi), "f"(elo));
   return p;
 }
 
@@ -306,66 +305,91 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
         }
       }
     } else if (warp == 1 && lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc_pv = make_idesc_f16(kBQ, kHD, 0, 1);   // B (=V) is MN-major
-      constexpr uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0);
+      // ===== MMA issuer 1: S_X(j) = Q_X K_j^T for both query tiles =====
       const uint64_t qdesc[2] = {make_smem_desc_sw128(smem_u32(sQ)),
                                  make_smem_desc_sw128(smem_u32(sQ + kQBytes))};
-      const uint32_t ones_addr = smem_u32(sOnes);
-      int kstage = 0, vstage = 0;
-      uint32_t kphase = 0, vphase = 0, item_phase = 0;
+      uint64_t kdesc[kKVStages];
+#pragma unroll
+      for (int st = 0; st < kKVStages; ++st) kdesc[st] = make_smem_desc_sw128(smem_u32(sK + st * kKBytes));
+      constexpr uint32_t idesc_full = make_idesc_f16(kBQ, kBKV, 0, 0);
+      const uint32_t idesc_last = make_idesc_f16(kBQ, last_len, 0, 0);
+      int kstage = 0;
+      uint32_t kphase = 0, item_phase = 0;
       uint32_t blk = 0;   // running count of key blocks processed by this CTA (barrier parity)
       for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
         mbar_wait(&bars->q_full, item_phase);
         item_phase ^= 1;
-        tc_fence_after_sync();
-        for (int j = 0; j <= num_kv; ++j) {
-          if (j < num_kv) {
-            const int len = (j == num_kv - 1) ? last_len : kBKV;
-            const uint32_t idesc_s = make_idesc_f16(kBQ, len, 0, 0);
-            const uint32_t par = (blk + j) & 1;
-            mbar_wait(&bars->k_full[kstage], kphase);
-            const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + kstage * kKBytes));
+        for (int j = 0; j < num_kv; ++j) {
+          const uint32_t idesc_s = (j == num_kv - 1) ? idesc_last : idesc_full;
+          const uint32_t par = (blk + j) & 1;
+          mbar_wait(&bars->k_full[kstage], kphase);
+          const uint64_t kd = kdesc[kstage];
 #pragma unroll
-            for (int x = 0; x < 2; ++x) {
-              mbar_wait(&bars->s_empty[x], par ^ 1);
-              tc_fence_after_sync();
+          for (int x = 0; x < 2; ++x) {
+            mbar_wait(&bars->s_empty[x], par ^ 1);
+            tc_fence_after_sync();
 #pragma unroll
-              for (int k = 0; k < kHD / 16; ++k)
-                umma_f16_ss(tmem_base + kColS + x * kBKV, qdesc[x] + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-              umma_commit(&bars->s_full[x]);
-            }
-            umma_commit(&bars->k_empty[kstage]);
-            if (j == num_kv - 1) umma_commit(&bars->q_empty);   // Q tiles may be overwritten
-            if (++kstage == kKVStages) { kstage = 0; kphase ^= 1; }
+            for (int k = 0; k < kHD / 16; ++k)
+              umma_f16_ss(tmem_base + kColS + x * kBKV, qdesc[x] + 2 * k, kd + 2 * k, idesc_s, k != 0);
+            umma_commit(&bars->s_full[x]);
           }
-          if (j >= 1) {
-            const int jj = j - 1;
-            const int len = (jj == num_kv - 1) ? last_len : kBKV;
-            const uint32_t par = (blk + jj) & 1;
-            mbar_wait(&bars->v_full[vstage], vphase);
-            const uint32_t v_addr = smem_u32(sV + vstage * kVBytes);
+          umma_commit(&bars->k_empty[kstage]);
+          if (j == num_kv - 1) umma_commit(&bars->q_empty);   // Q tiles may be overwritten
+          if (++kstage == kKVStages) { kstage = 0; kphase ^= 1; }
+        }
+        blk += num_kv;
+      }
+    } else if (warp == 3 && lane == 0) {
+      // ===== MMA issuer 2: PV_X(j) = P_X(j) V_j and the row sums L_X(j) = P_X(j) 1 =====
+      constexpr uint32_t idesc_pv = make_idesc_f16(kBQ, kHD, 0, 1);   // B (=V) is MN-major
+      constexpr uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0);
+      // A = P: K-major, two 64-key atoms of 16 KB; +32 B (= +2) per 16 keys inside an atom.
+      const uint64_t pdesc[2] = {make_smem_desc_sw128(smem_u32(sP)),
+                                 make_smem_desc_sw128(smem_u32(sP + kPBytes))};
+      // B = V: MN-major, 16 key rows of 128 B (= +128 in the address field) per K step.
+      uint64_t vdesc[kKVStages];
+#pragma unroll
+      for (int st = 0; st < kKVStages; ++st) vdesc[st] = make_smem_desc_sw128(smem_u32(sV + st * kVBytes));
+      const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes));
+      int vstage = 0;
+      uint32_t vphase = 0;
+      uint32_t blk = 0;
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+        for (int j = 0; j < num_kv; ++j) {
+          const uint32_t par = (blk + j) & 1;
+          const uint32_t acc0 = j != 0;          // the first block of an item overwrites O / L
+          mbar_wait(&bars->v_full[vstage], vphase);
+          const uint64_t vd = vdesc[vstage];
+          if (j < num_kv - 1 || last_len == kBKV) {
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
               mbar_wait(&bars->p_full[x], par);
               tc_fence_after_sync();
-              const uint32_t p_addr = smem_u32(sP + x * kPBytes);
-              for (int k = 0; k < len / 16; ++k) {
-                // A = P: K-major, two 64-key atoms of 16 KB; +32 B per 16 keys inside an atom.
-                const uint64_t pdesc =
-                    make_smem_desc_sw128(p_addr + (k >> 2) * (kBQ * 128) + (k & 3) * 32);
-                // B = V: MN-major, 16 key rows of 128 B per K step.
-                const uint64_t vdesc = make_smem_desc_sw128(v_addr + k * 2048);
-                umma_f16_ss(tmem_base + kColPV + x * kHD, pdesc, vdesc, idesc_pv, (jj | k) != 0);
-                // Row sums of P: B = ones (16 x 16 keys per step).
-                const uint64_t odesc = make_smem_desc_sw128(ones_addr + (k & 3) * 32);
-                umma_f16_ss(tmem_base + kColL + x * 16, pdesc, odesc, idesc_l, (jj | k) != 0);
+#pragma unroll
+              for (int k = 0; k < kBKV / 16; ++k) {
+                const uint64_t pd = pdesc[x] + static_cast<uint64_t>((k >> 2) * (kBQ * 128 / 16) + (k & 3) * 2);
+                umma_f16_ss(tmem_base + kColPV + x * kHD, pd, vd + k * 128, idesc_pv, acc0 | (k != 0));
+                umma_f16_ss(tmem_base + kColL + x * 16, pd, odesc + (k & 3) * 2, idesc_l, acc0 | (k != 0));
               }
               umma_commit(&bars->pv_done[x]);
             }
-            umma_commit(&bars->v_empty[vstage]);
-            if (++vstage == kKVStages) { vstage = 0; vphase ^= 1; }
+          } else {
+            const int ksteps = last_len / 16;
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              mbar_wait(&bars->p_full[x], par);
+              tc_fence_after_sync();
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t pd = pdesc[x] + static_cast<uint64_t>((k >> 2) * (kBQ * 128 / 16) + (k & 3) * 2);
+                umma_f16_ss(tmem_base + kColPV + x * kHD, pd, vd + k * 128, idesc_pv, acc0 | (k != 0));
+                umma_f16_ss(tmem_base + kColL + x * 16, pd, odesc + (k & 3) * 2, idesc_l, acc0 | (k != 0));
+              }
+              umma_commit(&bars->pv_done[x]);
+            }
           }
+          umma_commit(&bars->v_empty[vstage]);
+          if (++vstage == kKVStages) { vstage = 0; vphase ^= 1; }
         }
         blk += num_kv;
       }
