@@ -15,11 +15,12 @@
 // Items may be produced on the device (knn_build_items_*), so the retrieval pipeline needs no
 // host synchronisation.
 //
-// CTA layout (256 threads, persistent over items):
+// CTA layout (384 threads, persistent over items):
 //   warp 0   TMA producer   (query k-block + bank-tile k-block per stage, 128B swizzle)
-//   warp 1   MMA issuer     (128 x 128 x 16 tcgen05.mma, accumulators double-buffered in TMEM)
+//   warp 1   MMA issuer     (128 x 256 x 16 tcgen05.mma, accumulators double-buffered in TMEM)
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue      (thread = query row: tcgen05.ld dots, d = ||x||^2 - 2 dot, sorted insert)
+//   warps 4-11 epilogue     (thread = query row x column half: tcgen05.ld dots, d = ||x||^2 - 2 dot,
+//                            tree argmin for k = 1 / prefiltered sorted insert for k > 1)
 #include "common.cuh"
 #include "kernels.h"
 
@@ -28,14 +29,16 @@ namespace fp {
 namespace {
 
 constexpr int BQ = 128;   // query rows per item
-constexpr int BX = 128;   // bank rows per tile
+constexpr int BX = 256;   // bank rows per tile (128 x 256 x 16 UMMA: 96 B/clk of smem operand reads)
 constexpr int BKK = 64;   // K elements per stage
-constexpr int kStages = 6;
+constexpr int kStages = 4;
+constexpr int kMaxK = 16;
+constexpr uint32_t kMergeBytes = BQ * kMaxK * 8;   // (dist, idx) lists of the second column half
 constexpr uint32_t kQStage = BQ * BKK * 2;
 constexpr uint32_t kXStage = BX * BKK * 2;
 constexpr uint32_t kStageBytes = kQStage + kXStage;
-constexpr uint32_t kKnnSmem = kStages * kStageBytes + 256 + 1024;
-constexpr int kKnnThreads = 256;
+constexpr uint32_t kKnnSmem = kStages * kStageBytes + kMergeBytes + 256 + 1024;
+constexpr int kKnnThreads = 384;   // 4 control warps + 8 epilogue warps
 
 template <int K>
 struct TopK {
@@ -58,6 +61,16 @@ struct TopK {
       }
     }
   }
+  // Lexicographic (distance, index) insert: used when merging lists whose index ranges interleave.
+  __device__ __forceinline__ void push_lex(float cd, int ci) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (cd < d[j] || (cd == d[j] && ci < i[j])) {
+        const float td = d[j]; d[j] = cd; cd = td;
+        const int ti = i[j]; i[j] = ci; ci = ti;
+      }
+    }
+  }
 };
 
 template <int K>
@@ -69,7 +82,8 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* merge_buf = smem + kStages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(merge_buf + kMergeBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -87,7 +101,7 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
   } else if (warp == 2) {
@@ -156,9 +170,15 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     }
     __syncwarp();
   } else if (warp >= 4) {
+    // 8 epilogue warps: warp % 4 selects the TMEM sub-partition (32 query rows), (warp - 4) / 4 the
+    // half of the tile's 256 bank columns.  Each thread keeps the k best of ITS columns; the two
+    // halves are merged through shared memory once per item.
     const int sub = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int r = sub * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
+    float* merge_d = reinterpret_cast<float*>(merge_buf);
+    int* merge_i = reinterpret_cast<int*>(merge_buf + BQ * kMaxK * 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
@@ -170,23 +190,74 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       for (int t = 0; t < num_tiles; ++t) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
-        const int col_base = t * BX;
-        const int ncols = min(BX, item.b_rows - col_base);
+        const int col_base = t * BX + half * (BX / 2);
+        const int ncols = item.b_rows - col_base;          // valid columns in this half (may be <= 0)
         const float* xn = xnorm + item.b_row0 + col_base;
 #pragma unroll 1
-        for (int c = 0; c < BX / 32; ++c) {
+        for (int c = 0; c < BX / 64; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * BX + c * 32, v);
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * BX + half * (BX / 2) + c * 32, v);
           tmem_ld_wait();
           if (c * 32 < ncols) {
+            float dist[32];
+            if (c * 32 + 32 <= ncols) {
+              // L2: ||x||^2 - 2<q,x> (||q||^2 is added once at the end); IP: -<q,x>.
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = c * 32 + i;
-              if (col < ncols) {
-                const float dot = __uint_as_float(v[i]);
-                // L2: ||x||^2 - 2<q,x> (||q||^2 is added once at the end); IP: -<q,x>.
-                const float cand = metric_ip ? -dot : fmaf(-2.0f, dot, __ldg(xn + col));
-                best.push(cand, col_base + col);
+              for (int g = 0; g < 8; ++g) {
+                float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!metric_ip) {
+                  // xnorm rows are only 4-byte aligned in general (segment starts are arbitrary).
+                  n4.x = __ldg(xn + c * 32 + g * 4 + 0); n4.y = __ldg(xn + c * 32 + g * 4 + 1);
+                  n4.z = __ldg(xn + c * 32 + g * 4 + 2); n4.w = __ldg(xn + c * 32 + g * 4 + 3);
+                }
+                dist[g * 4 + 0] = metric_ip ? -__uint_as_float(v[g * 4 + 0]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 0]), n4.x);
+                dist[g * 4 + 1] = metric_ip ? -__uint_as_float(v[g * 4 + 1]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 1]), n4.y);
+                dist[g * 4 + 2] = metric_ip ? -__uint_as_float(v[g * 4 + 2]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 2]), n4.z);
+                dist[g * 4 + 3] = metric_ip ? -__uint_as_float(v[g * 4 + 3]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 3]), n4.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int col = c * 32 + i;
+                float dv = INFINITY;
+                if (col < ncols) {
+                  const float dot = __uint_as_float(v[i]);
+                  dv = metric_ip ? -dot : fmaf(-2.0f, dot, __ldg(xn + col));
+                }
+                dist[i] = dv;
+              }
+            }
+            if constexpr (K == 1) {
+              // argmin of the 32 candidates by a tree (depth 5) instead of a 32-deep serial chain;
+              // the left operand (lower index) wins ties.
+              int idx[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool lt = dist[2 * i + 1] < dist[2 * i];
+                dist[i] = lt ? dist[2 * i + 1] : dist[2 * i];
+                idx[i] = lt ? 2 * i + 1 : 2 * i;
+              }
+#pragma unroll
+              for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+                for (int i = 0; i < w; ++i) {
+                  const bool lt = dist[2 * i + 1] < dist[2 * i];
+                  dist[i] = lt ? dist[2 * i + 1] : dist[2 * i];
+                  idx[i] = lt ? idx[2 * i + 1] : idx[2 * i];
+                }
+              }
+              if (dist[0] < best.d[0]) {
+                best.d[0] = dist[0];
+                best.i[0] = col_base + c * 32 + idx[0];
+              }
+            } else {
+              // Cheap prefilter: skip the chunk when nothing beats the current k-th best.
+              float cmin = dist[0];
+#pragma unroll
+              for (int i = 1; i < 32; ++i) cmin = fminf(cmin, dist[i]);
+              if (cmin < best.d[K - 1]) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) best.push(dist[i], col_base + c * 32 + i);
               }
             }
           }
@@ -197,21 +268,35 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      if (r < item.q_rows) {
-        const long row = static_cast<long>(item.out_row0) + r;
-        const float qn = metric_ip ? 0.f : qnorm[static_cast<long>(item.q_row0) + r];
+      // Merge the two column halves (their index ranges interleave tile by tile -> lexicographic).
+      if (half == 1) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-          if (j < k_out) {
-            float dv;
-            if (metric_ip) dv = -best.d[j];                 // similarity, descending
-            else dv = fmaxf(best.d[j] + qn, 0.f);           // faiss clamps negative distances to 0
-            if (best.i[j] < 0) dv = metric_ip ? -INFINITY : INFINITY;  // fewer than k bank rows
-            out_d[row * k_out + j] = dv;
-            out_i[row * k_out + j] = best.i[j];
+          merge_d[j * BQ + r] = best.d[j];
+          merge_i[j * BQ + r] = best.i[j];
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) best.push_lex(merge_d[j * BQ + r], merge_i[j * BQ + r]);
+        if (r < item.q_rows) {
+          const long row = static_cast<long>(item.out_row0) + r;
+          const float qn = metric_ip ? 0.f : qnorm[static_cast<long>(item.q_row0) + r];
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            if (j < k_out) {
+              float dv;
+              if (metric_ip) dv = -best.d[j];                 // similarity, descending
+              else dv = fmaxf(best.d[j] + qn, 0.f);           // faiss clamps negative distances to 0
+              if (best.i[j] < 0) dv = metric_ip ? -INFINITY : INFINITY;  // fewer than k bank rows
+              out_d[row * k_out + j] = dv;
+              out_i[row * k_out + j] = best.i[j];
+            }
           }
         }
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // merge buffer reusable
     }
   }
 
