@@ -134,6 +134,11 @@ int fp_gemm_tn_f16(int epilogue, const void* A, int lda, const void* B, int ldb,
                      ldb, p, static_cast<cudaStream_t>(stream));
 }
 
+int fp_gemm_force_1sm(int on) {
+  fp::gemm_force_1sm(on);
+  return 0;
+}
+
 int fp_umma_probe(const void* A, const void* B, float* out, int b_mn_major, void* stream) {
   return fp::umma_probe(static_cast<const __half*>(A), static_cast<const __half*>(B), out,
                         b_mn_major, static_cast<cudaStream_t>(stream));

@@ -271,6 +271,239 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// 2-CTA variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256
+// output tile.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256
+// weight rows); the pair's tensor cores read both halves, so per-SM shared-memory operand traffic
+// drops from 96 to 64 B/clk and the 128 B/clk port no longer throttles the MMA (see
+// profiles/r01_baseline_summary.md).  Only the leader CTA issues MMAs; completion is multicast to
+// both CTAs' barriers; both CTAs run their own TMA producer and epilogue warps.
+// ----------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the leader's copy
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// TMA load into this CTA's smem, completing on the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all prior MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 0x3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :
+      : "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// Arrive on the leader CTA's copy of a barrier (local arrive when executed by the leader).
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) &
+                                                                                   kPeerBitMask)
+               : "memory");
+}
+
+struct Gemm2Cfg {
+  static constexpr int kStages = 6;
+  static constexpr int BN = 256;                       // output tile columns (pair)
+  static constexpr uint32_t kABytes = BM * BK * 2;     // 16 KB: this CTA's 128 rows of A
+  static constexpr uint32_t kBBytes = 128 * BK * 2;    // 16 KB: this CTA's half of the B tile
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 512;           // 2 accumulators x 256 columns
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 256 + 1024;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int BN = Cfg::BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();        // 0 = leader (issues the MMAs)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);                 // leader: one arrive.expect_tx for both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);                // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);                // multicast tcgen05.commit
+      mbar_init(&tempty_bar[a], 2 * kEpilogueWarps);   // leader: epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / BK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m_blk = t / num_n;
+        const int n_blk = t - m_blk * num_n;
+        const int row_a = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+        const int row_b = n_blk * BN + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, row_a);
+          tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, row_b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int sub = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int m_blk = t / num_n;
+      const int n_blk = t - m_blk * num_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const int row = m_blk * 2 * BM + static_cast<int>(rank) * BM + sub * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int col0 = half * (BN / 2) + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + col0, r);
+        tmem_ld_wait();
+        if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  // Neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers.
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int EPI>
+int launch_2sm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  static bool configured = false;
+  if (!configured) {
+    FP_CUDA_CHECK(cudaFuncSetAttribute(gemm2_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / Cfg::BN);
+  int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
+  ProfScope prof(PROF_GEMM, stream, 2.0 * p.M * p.N * p.K);
+  gemm2_tn_kernel<EPI><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 template <int BN, int EPI>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                cudaStream_t stream) {
@@ -299,6 +532,9 @@ int launch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 
 }  // namespace
 
+static bool g_force_1sm = false;
+void gemm_force_1sm(int on) { g_force_1sm = on != 0; }
+
 int gemm_pick_bn(int M, int N) {
   if (N % 256 != 0) return 128;
   // Prefer the 128x256 tile unless it quantises badly onto 148 SMs.
@@ -319,10 +555,21 @@ int gemm_tn(int epi, const __half* A, int lda, const __half* B, int ldb, const G
   FP_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm_tn: leading dimensions must be multiples of 8");
   FP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
              "gemm_tn: operands must be 16-byte aligned");
-  const int bn = gemm_pick_bn(p.M, p.N);
+  const bool use_2sm = (p.N % 256 == 0) && (p.M > 256) && !g_force_1sm;
+  const int bn = use_2sm ? 128 : gemm_pick_bn(p.M, p.N);   // 2-CTA: each CTA stages 128 B rows
   CUtensorMap tmA, tmB;
   if (make_tma_2d_f16(&tmA, A, p.M, p.K, lda, BM) != 0) return 3;
   if (make_tma_2d_f16(&tmB, B, p.N, p.K, ldb, bn) != 0) return 3;
+  if (use_2sm) {
+    switch (epi) {
+      case EPI_BIAS_F16: return launch_2sm<EPI_BIAS_F16>(tmA, tmB, p, stream);
+      case EPI_BIAS_GELU_F16: return launch_2sm<EPI_BIAS_GELU_F16>(tmA, tmB, p, stream);
+      case EPI_RESID_F32: return launch_2sm<EPI_RESID_F32>(tmA, tmB, p, stream);
+      case EPI_PATCH_F32: return launch_2sm<EPI_PATCH_F32>(tmA, tmB, p, stream);
+      case EPI_BIAS_F32: return launch_2sm<EPI_BIAS_F32>(tmA, tmB, p, stream);
+      default: set_last_error("gemm_tn: unknown epilogue %d", epi); return 1;
+    }
+  }
   switch (epi) {
     case EPI_BIAS_F16: return launch_bn<EPI_BIAS_F16>(bn, tmA, tmB, p, stream);
     case EPI_BIAS_GELU_F16: return launch_bn<EPI_BIAS_GELU_F16>(bn, tmA, tmB, p, stream);

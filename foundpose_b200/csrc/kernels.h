@@ -34,6 +34,7 @@ struct GemmParams {
 };
 
 int gemm_pick_bn(int M, int N);
+void gemm_force_1sm(int on);   // A/B switch: disable the cta_group::2 kernel
 int gemm_tn(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
             cudaStream_t stream);
 int umma_probe(const __half* A, const __half* B, float* out, int b_mn_major, cudaStream_t stream);

@@ -43,6 +43,10 @@ int fp_gemm_tn_f16(int epilogue, const void* A, int lda, const void* B, int ldb,
                    int K, const float* bias, const float* gamma, void* out_f16, int ld_f16,
                    float* out_f32, int ld_f32, void* stream);
 
+/* A/B switch for benchmarking: 1 = always use the 1-CTA kernel instead of the cta_group::2 pair
+ * kernel (default 0). */
+int fp_gemm_force_1sm(int on);
+
 /* Single-tile UMMA descriptor probe used by the GPU tests (not on the hot path). */
 int fp_umma_probe(const void* A, const void* B, float* out, int b_mn_major, void* stream);
 
