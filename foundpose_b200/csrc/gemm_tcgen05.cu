@@ -41,24 +41,11 @@ struct GemmCfg {
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 1024 /*align*/;
 };
 
-// Exact (erf) GELU as torch.nn.GELU() computes it (external/dinov2/dinov2/layers/mlp.py:36),
-// with erf evaluated by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the fp16
-// rounding of the stored activation): 2 MUFU + ~12 FP32 ops instead of the ~25 of erff(), which
-// made the fc1 epilogue as long as its 1024-deep main loop.
+// Exact (erf) GELU as torch.nn.GELU() computes it (external/dinov2/dinov2/layers/mlp.py:36).
+// (An Abramowitz-Stegun erf with 2 MUFU ops per element was measured slower than erff() here: the
+// step is power-capped and the extra MUFU traffic costs more than the saved FP32 instructions.)
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  // exp(-z^2) = exp2(-z^2 * log2(e))
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x| / sqrt(2))
-  const float half_x = 0.5f * x;
-  return fmaf(half_x, copysignf(erf_abs, x), half_x);  // 0.5 x (1 + erf(x / sqrt(2)))
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
 template <int EPI>
@@ -152,19 +139,6 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, int row, i
         pk.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(d16 + j * 8) = pk;
       }
-    }
-  }
-}
-
-// EPI_RESID_F32 reads and rewrites the fp32 residual stream: pull the 512 bytes of x this thread
-// will need for the next tile into L2 while the tile's main loop is still running, so the epilogue
-// pays an L2 hit instead of a full HBM round trip per 32-column chunk.
-template <int EPI>
-__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, int row, int n0, int ncols) {
-  if constexpr (EPI == EPI_RESID_F32) {
-    if (row < p.M) {
-      const float* src = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + n0;
-      for (int c = 0; c < ncols; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + c));
     }
   }
 }
@@ -273,7 +247,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = t / num_n;
       const int n_blk = t - m_blk * num_n;
       const int row = m_blk * BM + sub * 32 + lane;
-      epilogue_prefetch<EPI>(p, row, n_blk * BN + half * (BN / 2), BN / 2);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
@@ -489,7 +462,6 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = t / num_n;
       const int n_blk = t - m_blk * num_n;
       const int row = m_blk * 2 * BM + static_cast<int>(rank) * BM + sub * 32 + lane;
-      epilogue_prefetch<EPI>(p, row, n_blk * BN + half * (BN / 2), BN / 2);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
@@ -564,7 +536,8 @@ int launch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 }  // namespace
 
 static bool g_force_1sm = false;
-void gemm_force_1sm(int on) { g_force_1sm = on != 0; }
+static int g_tuning_flags = 0;   // spare A/B switches for experiments (GemmParams::flags)
+void gemm_force_1sm(int on) { g_force_1sm = (on & 1) != 0; g_tuning_flags = on >> 1; }
 
 int gemm_pick_bn(int M, int N) {
   if (N % 256 != 0) return 128;
@@ -578,8 +551,10 @@ int gemm_pick_bn(int M, int N) {
   return (eff128 > eff256 + 0.04) ? 128 : 256;
 }
 
-int gemm_tn(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
+int gemm_tn(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p_in,
             cudaStream_t stream) {
+  GemmParams p = p_in;
+  p.flags = g_tuning_flags;
   FP_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_tn: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   FP_REQUIRE(p.N % 128 == 0, "gemm_tn: N=%d must be a multiple of 128", p.N);
   FP_REQUIRE(p.K % BK == 0, "gemm_tn: K=%d must be a multiple of %d", p.K, BK);

@@ -31,6 +31,7 @@ struct GemmParams {
   int tokens_per_img = 1;
   int tok_off = 0;
   const float* pos = nullptr;    // [patches_per_img, N] fp32
+  int flags = 0;                 // A/B tuning switches (see gemm_force_1sm)
 };
 
 int gemm_pick_bn(int M, int N);
