@@ -1,0 +1,61 @@
+"""The infer.py entry point on the GPU: the reference-style per-crop loop and the batched pipeline
+must produce the same correspondences; unsorted template ids go through the feature permutation."""
+import pytest
+import torch
+
+from foundpose_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def test_per_crop_and_batched_modes_agree(monkeypatch):
+    from foundpose_b200.scripts import infer
+
+    monkeypatch.setenv("FOUNDPOSE_SYNTHETIC_WEIGHTS", "5")
+    opts = infer.InferOpts(extractor_name="dinov2_version=tiny-test-reg_stride=14_facet=token_layer=2_norm=1",
+                           grid_cell_size=14.0, crop_size=(112, 112), match_top_n_templates=3,
+                           match_top_k_buddies=25, debug=False)
+    a = infer.infer(opts, num_synthetic_crops=5, batch=0, synthetic_bank=(12, 40, 128, 32))
+    b = infer.infer(opts, num_synthetic_crops=5, batch=4, synthetic_bank=(12, 40, 128, 32))
+    assert len(a) == len(b) == 5
+    for ra, rb in zip(a, b):
+        assert ra["crop_id"] == rb["crop_id"]
+        if len(ra["corresp"]) == 0:          # empty mask -> the per-crop path returns no correspondences
+            assert all(len(c["coord_2d"]) == 0 for c in rb["corresp"])
+            continue
+        for ca, cb in zip(ra["corresp"], rb["corresp"]):
+            assert int(ca["template_id"]) == int(cb["template_id"])
+            assert torch.equal(ca["coord_2d_ids"], cb["coord_2d_ids"])
+            assert torch.equal(ca["nn_vertex_ids"], cb["nn_vertex_ids"])
+            assert torch.allclose(ca["coord_3d"], cb["coord_3d"])
+
+
+def test_unsorted_template_ids_use_the_permutation():
+    from foundpose_b200 import pipeline
+    from foundpose_b200.utils import corresp_util, knn_util, repre_util, template_util
+    from oracle import corresp as ocorresp
+
+    bank = synthetic.make_bank_tensors(10, 30, 64, num_words=16, seed=4, ragged=True)
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(bank["feat_vectors"].shape[0], generator=g)
+    feat, tpl, verts = bank["feat_vectors"][perm], bank["feat_to_template_ids"][perm], bank["vertices"][perm]
+    wk = knn_util.KNN(1, "l2"); wk.fit(bank["feat_cluster_centroids"].cuda())
+    f2w = wk.search(feat.cuda())[1].flatten()
+    descs, idfs = template_util.calc_tfidf_descriptors(feat.cuda(), f2w, tpl.cuda(), bank["feat_cluster_centroids"].cuda(),
+                                                       10, 3, False, 10.0)
+    repre = repre_util.FeatureBasedObjectRepre(
+        vertices=verts, feat_vectors=feat, feat_to_template_ids=tpl, feat_cluster_centroids=bank["feat_cluster_centroids"],
+        feat_cluster_idfs=idfs.cpu(), template_descs=descs.cpu(), template_desc_opts=repre_util.TemplateDescOpts())
+    index = pipeline.get_object_index(repre, torch.device("cuda"))
+    assert index.feat_perm is not None
+    q = synthetic.make_query_features(60, 64, feat, seed=9)
+    pts = torch.rand(60, 2, generator=g) * 100
+    ours = corresp_util.establish_correspondences(pts.cuda(), q.cuda(), repre, "tfidf", "cyclic_buddies", 3, 20, wk, None, True)
+    ref = ocorresp.establish_correspondences(pts, q, {
+        "feat_vectors": feat, "feat_to_template_ids": tpl, "vertices": verts,
+        "feat_cluster_centroids": bank["feat_cluster_centroids"], "feat_cluster_idfs": idfs.cpu(),
+        "template_descs": descs.cpu()}, 3, 20)
+    for a, b in zip(ours, ref):
+        assert int(a["template_id"]) == int(b["template_id"])
+        assert torch.equal(a["nn_vertex_ids"].cpu(), b["nn_vertex_ids"])      # original feature ids
+        assert torch.equal(a["coord_3d"].cpu(), b["coord_3d"])
