@@ -35,7 +35,7 @@ def test_unsorted_template_ids_use_the_permutation():
     from foundpose_b200.utils import corresp_util, knn_util, repre_util, template_util
     from oracle import corresp as ocorresp
 
-    bank = synthetic.make_bank_tensors(10, 30, 64, num_words=16, seed=4, ragged=True)
+    bank = synthetic.make_bank_tensors(10, 30, 64, num_words=64, seed=4, ragged=True)
     g = torch.Generator().manual_seed(0)
     perm = torch.randperm(bank["feat_vectors"].shape[0], generator=g)
     feat, tpl, verts = bank["feat_vectors"][perm], bank["feat_to_template_ids"][perm], bank["vertices"][perm]
@@ -50,11 +50,17 @@ def test_unsorted_template_ids_use_the_permutation():
     assert index.feat_perm is not None
     q = synthetic.make_query_features(60, 64, feat, seed=9)
     pts = torch.rand(60, 2, generator=g) * 100
-    ours = corresp_util.establish_correspondences(pts.cuda(), q.cuda(), repre, "tfidf", "cyclic_buddies", 3, 20, wk, None, True)
+    k3 = knn_util.KNN(3, "l2"); k3.fit(bank["feat_cluster_centroids"].cuda())   # k comes from the index, as in the reference
+    ours = corresp_util.establish_correspondences(pts.cuda(), q.cuda(), repre, "tfidf", "cyclic_buddies", 3, 20, k3, None, True)
     ref = ocorresp.establish_correspondences(pts, q, {
         "feat_vectors": feat, "feat_to_template_ids": tpl, "vertices": verts,
         "feat_cluster_centroids": bank["feat_cluster_centroids"], "feat_cluster_idfs": idfs.cpu(),
         "template_descs": descs.cpu()}, 3, 20)
+    from oracle import template as otemplate
+
+    _, _, _, cos = otemplate.tfidf_matching(q, bank["feat_cluster_centroids"], idfs.cpu(), descs.cpu(), 3)
+    top = torch.sort(cos, descending=True).values
+    assert float((top[:3] - top[1:4]).min()) > 1e-5, "test data has a near-tie in the retrieval scores"
     for a, b in zip(ours, ref):
         assert int(a["template_id"]) == int(b["template_id"])
         assert torch.equal(a["nn_vertex_ids"].cpu(), b["nn_vertex_ids"])      # original feature ids
