@@ -283,4 +283,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int a_mn_maj
 int make_tma_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                     uint32_t box_rows, uint32_t box_cols = 64);
 
+int make_tma_2d_f32_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_rows);
+
 }  // namespace fp

@@ -344,28 +344,49 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
                : "memory");
 }
 
+template <int EPI>
 struct Gemm2Cfg {
-  static constexpr int kStages = 6;
+  // The residual epilogue stages its output through shared memory for TMA reduce-add stores
+  // (8 epilogue warps x 2 buffers x 4 KB), paid for with one pipeline stage.
+  static constexpr bool kTmaReduce = (EPI == EPI_RESID_F32);
+  static constexpr int kStages = kTmaReduce ? 5 : 6;
   static constexpr int BN = 256;                       // output tile columns (pair)
   static constexpr uint32_t kABytes = BM * BK * 2;     // 16 KB: this CTA's 128 rows of A
   static constexpr uint32_t kBBytes = 128 * BK * 2;    // 16 KB: this CTA's half of the B tile
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 512;           // 2 accumulators x 256 columns
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr uint32_t kStagingBytes = kTmaReduce ? kEpilogueWarps * 2 * 4096 : 0;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
+
+// x[rows, cols] += tile: fp32 add performed by the TMA / L2 (cp.reduce.async.bulk.tensor).  The SM
+// never loads the residual stream, so the epilogue has no global-load latency on its critical path,
+// and rows past M are clipped by the tensor map.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const GemmParams p) {
-  using Cfg = Gemm2Cfg;
+                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using Cfg = Gemm2Cfg<EPI>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int BN = Cfg::BN;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* staging = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -461,7 +482,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int m_blk = t / num_n;
       const int n_blk = t - m_blk * num_n;
-      const int row = m_blk * 2 * BM + static_cast<int>(rank) * BM + sub * 32 + lane;
+      const int row0 = m_blk * 2 * BM + static_cast<int>(rank) * BM + sub * 32;
+      const int row = row0 + lane;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
@@ -471,7 +493,32 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + col0, r);
         tmem_ld_wait();
-        if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r);
+        if constexpr (Cfg::kTmaReduce) {
+          // y = gamma * (acc + bias) -> 128B-swizzled 32 x 32 fp32 block in smem -> TMA reduce-add.
+          const int n0 = n_blk * BN + col0;
+          uint8_t* buf = staging + (warp - 4) * 8192 + (c & 1) * 4096;
+          if (lane == 0) tma_store_wait_read<1>();   // the store that last read this buffer is done
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j * 4));
+            float4 y;
+            y.x = g.x * (__uint_as_float(r[j * 4 + 0]) + b.x);
+            y.y = g.y * (__uint_as_float(r[j * 4 + 1]) + b.y);
+            y.z = g.z * (__uint_as_float(r[j * 4 + 2]) + b.z);
+            y.w = g.w * (__uint_as_float(r[j * 4 + 3]) + b.w);
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = y;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmC, buf, n0, row0);
+            tma_store_commit();
+          }
+        } else {
+          if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -481,6 +528,9 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
+  if constexpr (Cfg::kTmaReduce) {
+    if (warp >= 4 && lane == 0) tma_store_wait_read<0>();   // smem must outlive the bulk reads
+  }
   // Neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers.
   tc_fence_before_sync();
   cluster_sync_all();
@@ -492,7 +542,11 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 template <int EPI>
 int launch_2sm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<EPI>;
+  CUtensorMap tmC = tmA;   // only read by the TMA reduce-add epilogue
+  if (Cfg::kTmaReduce) {
+    if (make_tma_2d_f32_sw128(&tmC, p.out_f32, p.M, p.N, p.ld_f32, 32) != 0) return 3;
+  }
   static bool configured = false;
   if (!configured) {
     FP_CUDA_CHECK(cudaFuncSetAttribute(gemm2_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -502,7 +556,7 @@ int launch_2sm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
   const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / Cfg::BN);
   int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
   ProfScope prof(PROF_GEMM, stream, 2.0 * p.M * p.N * p.K);
-  gemm2_tn_kernel<EPI><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm2_tn_kernel<EPI><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -609,6 +663,27 @@ static PFN_tensorMapEncodeTiled get_encode_fn() {
     fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(ptr);
   }
   return fn;
+}
+
+// fp32 row-major [rows, cols], box [box_rows, 32 columns = 128 bytes], 128B swizzle.
+int make_tma_2d_f32_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_rows) {
+  PFN_tensorMapEncodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return 3;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(f32) failed (%d): base=%p rows=%llu cols=%llu ld=%llu",
+                   static_cast<int>(r), base, (unsigned long long)rows, (unsigned long long)cols,
+                   (unsigned long long)ld);
+    return 3;
+  }
+  return 0;
 }
 
 int make_tma_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
