@@ -42,10 +42,27 @@ struct GemmCfg {
 };
 
 // Exact (erf) GELU as torch.nn.GELU() computes it (external/dinov2/dinov2/layers/mlp.py:36).
-// (An Abramowitz-Stegun erf with 2 MUFU ops per element was measured slower than erff() here: the
-// step is power-capped and the extra MUFU traffic costs more than the saved FP32 instructions.)
-__device__ __forceinline__ float gelu_erf(float x) {
+__device__ __forceinline__ float gelu_erf_libm(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+// Same function with erf evaluated by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7 plus the
+// approximate reciprocal / exp2, together < 1e-6: far below the fp16 rounding of the stored
+// activation).  ~14 FP32 ops + 2 MUFU per element instead of erff()'s branchy ~50.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;   // exp(-z^2) = exp2(-z^2 * log2(e))
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x| / sqrt(2))
+  const float half_x = 0.5f * x;
+  return fmaf(half_x, copysignf(erf_abs, x), half_x);  // 0.5 x (1 + erf(x / sqrt(2)))
 }
 
 template <int EPI>
@@ -349,13 +366,18 @@ struct Gemm2Cfg {
   // The residual epilogue stages its output through shared memory for TMA reduce-add stores
   // (8 epilogue warps x 2 buffers x 4 KB), paid for with one pipeline stage.
   static constexpr bool kTmaReduce = (EPI == EPI_RESID_F32);
-  static constexpr int kStages = kTmaReduce ? 5 : 6;
+  // fp16 outputs (qkv, fc1) leave through smem + TMA stores as well: per-thread 16-byte global
+  // stores of a row-per-thread fragment (half sectors, 32 rows per instruction) were measured to
+  // cost 70-100 us per GEMM; the TMA writes whole 128-byte lines asynchronously.
+  static constexpr bool kTmaStore16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
+  static constexpr bool kStaged = kTmaReduce || kTmaStore16;
+  static constexpr int kStages = kStaged ? 5 : 6;
   static constexpr int BN = 256;                       // output tile columns (pair)
   static constexpr uint32_t kABytes = BM * BK * 2;     // 16 KB: this CTA's 128 rows of A
   static constexpr uint32_t kBBytes = 128 * BK * 2;    // 16 KB: this CTA's half of the B tile
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 512;           // 2 accumulators x 256 columns
-  static constexpr uint32_t kStagingBytes = kTmaReduce ? kEpilogueWarps * 2 * 4096 : 0;
+  static constexpr uint32_t kStagingBytes = kStaged ? kEpilogueWarps * 2 * 4096 : 0;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
 
@@ -364,6 +386,12 @@ struct Gemm2Cfg {
 // and rows past M are clipped by the tensor map.
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                :
                : "l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
@@ -487,6 +515,55 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
+      if constexpr (Cfg::kTmaStore16) {
+        // Two 32 x 64 fp16 blocks per warp: TMEM -> bias (+GELU) -> 128B-swizzled smem -> TMA store.
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+          const int col0 = half * (BN / 2) + blk * 64;
+          const int n0 = n_blk * BN + col0;
+          uint32_t r[64];
+          uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+          uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+          tmem_ld_32x32b_x32(taddr + col0, r0);
+          tmem_ld_32x32b_x32(taddr + col0 + 32, r1);
+          tmem_ld_wait();
+          uint8_t* buf = staging + (warp - 4) * 8192 + blk * 4096;
+          if (lane == 0) tma_store_wait_read<1>();   // the store that last read this buffer is done
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 8 + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if constexpr (EPI == EPI_BIAS_GELU_F16) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+            }
+            uint4 pk;
+            __half2 h0 = __floats2half2_rn(v[0], v[1]);
+            __half2 h1 = __floats2half2_rn(v[2], v[3]);
+            __half2 h2 = __floats2half2_rn(v[4], v[5]);
+            __half2 h3 = __floats2half2_rn(v[6], v[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, n0, row0);
+            tma_store_commit();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         const int col0 = half * (BN / 2) + c * 32;
@@ -520,6 +597,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r);
         }
       }
+      }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -528,7 +606,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
-  if constexpr (Cfg::kTmaReduce) {
+  if constexpr (Cfg::kStaged) {
     if (warp >= 4 && lane == 0) tma_store_wait_read<0>();   // smem must outlive the bulk reads
   }
   // Neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers.
@@ -546,6 +624,11 @@ int launch_2sm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
   CUtensorMap tmC = tmA;   // only read by the TMA reduce-add epilogue
   if (Cfg::kTmaReduce) {
     if (make_tma_2d_f32_sw128(&tmC, p.out_f32, p.M, p.N, p.ld_f32, 32) != 0) return 3;
+  }
+  if (Cfg::kTmaStore16) {
+    FP_REQUIRE(p.ld_f16 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_f16) & 15) == 0,
+               "gemm_tn: fp16 output must be 16-byte aligned with ld %% 8 == 0");
+    if (make_tma_2d_f16(&tmC, p.out_f16, p.M, p.N, p.ld_f16, 32, 64) != 0) return 3;
   }
   static bool configured = false;
   if (!configured) {

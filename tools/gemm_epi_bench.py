@@ -17,7 +17,8 @@ def rnd(*shape, scale=1.0):
     return (torch.randn(*shape, generator=g) * scale).half().cuda()
 
 
-cases = [("qkv  bias_f16", 3072, 1024, _native.EPI_BIAS_F16), ("qkv  nobias  ", 3072, 1024, -1),
+import ctypes
+cases = [ ("qkv  bias_f16", 3072, 1024, _native.EPI_BIAS_F16), ("qkv  nobias  ", 3072, 1024, -1),
          ("proj resid   ", 1024, 1024, _native.EPI_RESID_F32), ("proj bias_f16", 1024, 1024, _native.EPI_BIAS_F16),
          ("fc1  gelu    ", 4096, 1024, _native.EPI_BIAS_GELU_F16), ("fc1  bias_f16", 4096, 1024, _native.EPI_BIAS_F16),
          ("fc2  resid   ", 1024, 4096, _native.EPI_RESID_F32), ("fc2  bias_f16", 1024, 4096, _native.EPI_BIAS_F16)]
@@ -32,7 +33,15 @@ for name, n, k, epi in cases:
 
 def run(n, k, epi):
     b = bufs[(n, k)]
-    if epi == -1:
+    if epi == 101:
+        _native.load().fp_gemm_force_1sm(ctypes.c_int(4))
+        _native.gemm_tn_f16(b["a"], b["b"], _native.EPI_BIAS_GELU_F16, bias=b["bias"], out_f16=b["o16"])
+        _native.load().fp_gemm_force_1sm(ctypes.c_int(0))
+    elif epi == 102:
+        _native.load().fp_gemm_force_1sm(ctypes.c_int(8))
+        _native.gemm_tn_f16(b["a"], b["b"], _native.EPI_BIAS_F16, bias=b["bias"], out_f16=b["o16"])
+        _native.load().fp_gemm_force_1sm(ctypes.c_int(0))
+    elif epi == -1:
         _native.gemm_tn_f16(b["a"], b["b"], _native.EPI_BIAS_F16, out_f16=b["o16"])
     elif epi == _native.EPI_RESID_F32:
         _native.gemm_tn_f16(b["a"], b["b"], epi, bias=b["bias"], gamma=b["gamma"], out_f32=b["o32"])
