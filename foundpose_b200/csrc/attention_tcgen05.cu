@@ -324,14 +324,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
           const uint32_t par = (blk + j) & 1;
           mbar_wait(&bars->k_full[kstage], kphase);
           const uint64_t kd = kdesc[kstage];
+          // Serve whichever query tile frees its S buffer first: the two softmax warpgroups then
+          // stay half a block out of phase instead of being forced into lockstep.
+          uint32_t pending = 3;
+          uint32_t spins = 0;
+          while (pending) {
 #pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            mbar_wait(&bars->s_empty[x], par ^ 1);
-            tc_fence_after_sync();
+            for (int x = 0; x < 2; ++x) {
+              if ((pending >> x) & 1) {
+                if (mbar_try_wait(&bars->s_empty[x], par ^ 1)) {
+                  tc_fence_after_sync();
 #pragma unroll
-            for (int k = 0; k < kHD / 16; ++k)
-              umma_f16_ss(tmem_base + kColS + x * kBKV, qdesc[x] + 2 * k, kd + 2 * k, idesc_s, k != 0);
-            umma_commit(&bars->s_full[x]);
+                  for (int k = 0; k < kHD / 16; ++k)
+                    umma_f16_ss(tmem_base + kColS + x * kBKV, qdesc[x] + 2 * k, kd + 2 * k, idesc_s, k != 0);
+                  umma_commit(&bars->s_full[x]);
+                  pending &= ~(1u << x);
+                }
+              }
+            }
+            if (++spins > (1u << 28)) __trap();
           }
           umma_commit(&bars->k_empty[kstage]);
           if (j == num_kv - 1) umma_commit(&bars->q_empty);   // Q tiles may be overwritten
@@ -361,17 +372,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
           mbar_wait(&bars->v_full[vstage], vphase);
           const uint64_t vd = vdesc[vstage];
           if (j < num_kv - 1 || last_len == kBKV) {
+            uint32_t pending = 3;
+            uint32_t spins = 0;
+            while (pending) {
 #pragma unroll
-            for (int x = 0; x < 2; ++x) {
-              mbar_wait(&bars->p_full[x], par);
-              tc_fence_after_sync();
+              for (int x = 0; x < 2; ++x) {
+                if ((pending >> x) & 1) {
+                  if (mbar_try_wait(&bars->p_full[x], par)) {
+                    tc_fence_after_sync();
 #pragma unroll
-              for (int k = 0; k < kBKV / 16; ++k) {
-                const uint64_t pd = pdesc[x] + static_cast<uint64_t>((k >> 2) * (kBQ * 128 / 16) + (k & 3) * 2);
-                umma_f16_ss(tmem_base + kColPV + x * kHD, pd, vd + k * 128, idesc_pv, acc0 | (k != 0));
-                umma_f16_ss(tmem_base + kColL + x * 16, pd, odesc + (k & 3) * 2, idesc_l, acc0 | (k != 0));
+                    for (int k = 0; k < kBKV / 16; ++k) {
+                      const uint64_t pd = pdesc[x] + static_cast<uint64_t>((k >> 2) * (kBQ * 128 / 16) + (k & 3) * 2);
+                      umma_f16_ss(tmem_base + kColPV + x * kHD, pd, vd + k * 128, idesc_pv, acc0 | (k != 0));
+                      umma_f16_ss(tmem_base + kColL + x * 16, pd, odesc + (k & 3) * 2, idesc_l, acc0 | (k != 0));
+                    }
+                    umma_commit(&bars->pv_done[x]);
+                    pending &= ~(1u << x);
+                  }
+                }
               }
-              umma_commit(&bars->pv_done[x]);
+              if (++spins > (1u << 28)) __trap();
             }
           } else {
             const int ksteps = last_len / 16;
