@@ -134,6 +134,11 @@ int fp_gemm_tn_f16(int epilogue, const void* A, int lda, const void* B, int ldb,
                      ldb, p, static_cast<cudaStream_t>(stream));
 }
 
+int fp_attention_debug_buffer(void* device_buffer) {
+  fp::attention_set_debug_buffer(device_buffer);
+  return 0;
+}
+
 int fp_gemm_force_1sm(int on) {
   fp::gemm_force_1sm(on);
   return 0;

@@ -26,7 +26,22 @@
 
 namespace fp {
 
+static unsigned long long* g_attn_dbg = nullptr;   // timeline buffer (tools/attn_timeline.py)
+void attention_set_debug_buffer(void* p) { g_attn_dbg = static_cast<unsigned long long*>(p); }
+static int g_attn_flags = 0;   // experiment switches (tools/attn_bench.py); 0 in production
+void attention_set_flags(int f) { g_attn_flags = f; }
+
 namespace {
+
+// Timeline probe: CTA 0 only, role r in [0,5), up to 2048 events per role.
+__device__ __forceinline__ void dbg_event(unsigned long long* dbg, int role, int& n, int tag) {
+  if (dbg != nullptr && blockIdx.x == 0 && n < 2048) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[role * 2048 + n] = (static_cast<unsigned long long>(tag) << 48) | (t & 0xffffffffffffull);
+    ++n;
+  }
+}
 
 constexpr int kHD = 64;        // head dim (all DINOv2 variants)
 constexpr int kBQ = 128;       // queries per tile (two tiles per work item)
@@ -155,38 +170,54 @@ __device__ __forceinline__ float update_reference_max(AttnBars* bars, int x, uin
 }
 
 __device__ __forceinline__ void store_p8(uint8_t* prow, int r, int c, const uint32_t* s8, float scale_log2e,
-                                         float neg_m) {
+                                         float neg_m, int flags = 0) {
   uint4 pk;
+  if (flags & 1) {   // experiment: no MUFU
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(fmaf(__uint_as_float(s8[1]), scale_log2e, neg_m)), "f"(fmaf(__uint_as_float(s8[0]), scale_log2e, neg_m)));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(fmaf(__uint_as_float(s8[3]), scale_log2e, neg_m)), "f"(fmaf(__uint_as_float(s8[2]), scale_log2e, neg_m)));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk.z) : "f"(fmaf(__uint_as_float(s8[5]), scale_log2e, neg_m)), "f"(fmaf(__uint_as_float(s8[4]), scale_log2e, neg_m)));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk.w) : "f"(fmaf(__uint_as_float(s8[7]), scale_log2e, neg_m)), "f"(fmaf(__uint_as_float(s8[6]), scale_log2e, neg_m)));
+    const int atom = c >> 3, cc = c & 7;
+    if (!(flags & 2)) *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
+    return;
+  }
   pk.x = exp2_f16x2(fmaf(__uint_as_float(s8[0]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[1]), scale_log2e, neg_m));
   pk.y = exp2_f16x2(fmaf(__uint_as_float(s8[2]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[3]), scale_log2e, neg_m));
   pk.z = exp2_f16x2(fmaf(__uint_as_float(s8[4]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[5]), scale_log2e, neg_m));
   pk.w = exp2_f16x2(fmaf(__uint_as_float(s8[6]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[7]), scale_log2e, neg_m));
   // 128B swizzle: 16-byte chunk index XOR (row % 8); atom = c / 8.
   const int atom = c >> 3, cc = c & 7;
-  *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
+  if (!(flags & 2)) *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
 }
 
 // Full block: all 128 keys valid - fully static code, S held in registers (one TMEM pass).
 __device__ __forceinline__ void softmax_block_full(AttnBars* bars, int x, int lane, uint32_t tS, uint32_t tPV,
                                                    uint32_t tL, uint8_t* prow, int r, bool first,
-                                                   uint32_t par, float scale_log2e, float& m_used) {
+                                                   uint32_t par, float scale_log2e, float& m_used, int flags) {
   uint32_t s[kBKV];
+  if (flags & 16) {   // experiment: no TMEM read of S
+#pragma unroll
+    for (int i = 0; i < kBKV; ++i) s[i] = 0;
+  } else {
 #pragma unroll
   for (int c = 0; c < kBKV / 32; ++c) {
     uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
     tmem_ld_32x32b_x32(tS + c * 32, chunk);
   }
   tmem_ld_wait();
+  }
   tc_fence_before_sync();
   __syncwarp();
   if (lane == 0) mbar_arrive(&bars->s_empty[x]);   // S may be recomputed for the next block
   float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
+  if (!(flags & 4))
+#pragma unroll
   for (int i = 0; i < kBKV; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[i]));
   const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
   const float neg_m = update_reference_max(bars, x, tPV, tL, first, par, scale_log2e, m_blk, m_used);
 #pragma unroll
-  for (int c = 0; c < kBKV / 8; ++c) store_p8(prow, r, c, &s[c * 8], scale_log2e, neg_m);
+  for (int c = 0; c < kBKV / 8; ++c) store_p8(prow, r, c, &s[c * 8], scale_log2e, neg_m, flags);
 }
 
 // Last (partial) block: `len` (multiple of 16) columns were computed, keys >= valid are masked.
@@ -226,7 +257,7 @@ __device__ __forceinline__ void softmax_block_tail(AttnBars* bars, int x, int la
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int N, int D,
-                 int heads, int num_items, float scale_log2e) {
+                 int heads, int num_items, float scale_log2e, int flags, unsigned long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -282,133 +313,128 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
       int stage = 0;
       uint32_t phase = 0;
       uint32_t item_phase = 0;
+      int dn = 0;
       for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
         const int pair = it % pairs;
         const int head = (it / pairs) % heads;
         const int img = it / (pairs * heads);
         const int row_base = img * N;
         mbar_wait(&bars->q_empty, item_phase ^ 1);
+        dbg_event(dbg, 0, dn, 100);
         mbar_arrive_expect_tx(&bars->q_full, 2 * kQBytes);
         tma_load_2d(sQ, &tmQKV, &bars->q_full, head * kHD, row_base + pair * 2 * kBQ);
         tma_load_2d(sQ + kQBytes, &tmQKV, &bars->q_full, head * kHD, row_base + pair * 2 * kBQ + kBQ);
         item_phase ^= 1;
         for (int j = 0; j < num_kv; ++j) {
           mbar_wait(&bars->k_empty[stage], phase ^ 1);
+          dbg_event(dbg, 0, dn, 10 + j);
           mbar_arrive_expect_tx(&bars->k_full[stage], kKBytes);
           tma_load_2d(sK + stage * kKBytes, &tmQKV, &bars->k_full[stage], D + head * kHD,
                       row_base + j * kBKV);
           mbar_wait(&bars->v_empty[stage], phase ^ 1);
+          dbg_event(dbg, 0, dn, 30 + j);
           mbar_arrive_expect_tx(&bars->v_full[stage], kVBytes);
           tma_load_2d(sV + stage * kVBytes, &tmQKV, &bars->v_full[stage], 2 * D + head * kHD,
                       row_base + j * kBKV);
           if (++stage == kKVStages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ===== MMA issuer 1: S_X(j) = Q_X K_j^T for both query tiles =====
-      const uint64_t qdesc[2] = {make_smem_desc_sw128(smem_u32(sQ)),
-                                 make_smem_desc_sw128(smem_u32(sQ + kQBytes))};
-      uint64_t kdesc[kKVStages];
-#pragma unroll
-      for (int st = 0; st < kKVStages; ++st) kdesc[st] = make_smem_desc_sw128(smem_u32(sK + st * kKBytes));
+      // The WHOLE warp runs this loop with warp-uniform operands and one elected lane issues the
+      // MMAs: issuing tcgen05.mma from a divergent `lane == 0` branch makes the compiler wrap every
+      // instruction in a waterfall loop (R2UR.BROADCAST / BRA.U.ANY), ~90 cycles per MMA, which
+      // serialised the 24+ small MMAs of every key block (profiles/r01_attention_timeline.md).
+      const uint64_t qdesc0 = make_smem_desc_sw128(smem_u32(sQ));
+      const uint64_t qdesc1 = make_smem_desc_sw128(smem_u32(sQ + kQBytes));
+      const uint64_t kdesc0 = make_smem_desc_sw128(smem_u32(sK));
       constexpr uint32_t idesc_full = make_idesc_f16(kBQ, kBKV, 0, 0);
       const uint32_t idesc_last = make_idesc_f16(kBQ, last_len, 0, 0);
       int kstage = 0;
       uint32_t kphase = 0, item_phase = 0;
       uint32_t blk = 0;   // running count of key blocks processed by this CTA (barrier parity)
+      int dn = 0;
       for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
         mbar_wait(&bars->q_full, item_phase);
+        if (lane == 0) dbg_event(dbg, 1, dn, 100);
         item_phase ^= 1;
         for (int j = 0; j < num_kv; ++j) {
           const uint32_t idesc_s = (j == num_kv - 1) ? idesc_last : idesc_full;
           const uint32_t par = (blk + j) & 1;
           mbar_wait(&bars->k_full[kstage], kphase);
-          const uint64_t kd = kdesc[kstage];
-          // Serve whichever query tile frees its S buffer first: the two softmax warpgroups then
-          // stay half a block out of phase instead of being forced into lockstep.
-          uint32_t pending = 3;
-          uint32_t spins = 0;
-          while (pending) {
+          const uint64_t kd = kdesc0 + static_cast<uint64_t>(kstage * (kKBytes / 16));
 #pragma unroll
-            for (int x = 0; x < 2; ++x) {
-              if ((pending >> x) & 1) {
-                if (mbar_try_wait(&bars->s_empty[x], par ^ 1)) {
-                  tc_fence_after_sync();
+          for (int x = 0; x < 2; ++x) {
+            mbar_wait(&bars->s_empty[x], par ^ 1);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint64_t qd = x == 0 ? qdesc0 : qdesc1;
 #pragma unroll
-                  for (int k = 0; k < kHD / 16; ++k)
-                    umma_f16_ss(tmem_base + kColS + x * kBKV, qdesc[x] + 2 * k, kd + 2 * k, idesc_s, k != 0);
-                  umma_commit(&bars->s_full[x]);
-                  pending &= ~(1u << x);
-                }
-              }
+              for (int k = 0; k < kHD / 16; ++k)
+                umma_f16_ss(tmem_base + kColS + x * kBKV, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+              umma_commit(&bars->s_full[x]);
             }
-            if (++spins > (1u << 28)) __trap();
+            __syncwarp();
+            if (lane == 0) dbg_event(dbg, 1, dn, 40 + 20 * x + j);
           }
-          umma_commit(&bars->k_empty[kstage]);
-          if (j == num_kv - 1) umma_commit(&bars->q_empty);   // Q tiles may be overwritten
+          if (elect_one()) {
+            umma_commit(&bars->k_empty[kstage]);
+            if (j == num_kv - 1) umma_commit(&bars->q_empty);   // Q tiles may be overwritten
+          }
+          __syncwarp();
           if (++kstage == kKVStages) { kstage = 0; kphase ^= 1; }
         }
         blk += num_kv;
       }
-    } else if (warp == 3 && lane == 0) {
+    } else if (warp == 3) {
       // ===== MMA issuer 2: PV_X(j) = P_X(j) V_j and the row sums L_X(j) = P_X(j) 1 =====
       constexpr uint32_t idesc_pv = make_idesc_f16(kBQ, kHD, 0, 1);   // B (=V) is MN-major
       constexpr uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0);
       // A = P: K-major, two 64-key atoms of 16 KB; +32 B (= +2) per 16 keys inside an atom.
-      const uint64_t pdesc[2] = {make_smem_desc_sw128(smem_u32(sP)),
-                                 make_smem_desc_sw128(smem_u32(sP + kPBytes))};
+      const uint64_t pdesc0 = make_smem_desc_sw128(smem_u32(sP));
       // B = V: MN-major, 16 key rows of 128 B (= +128 in the address field) per K step.
-      uint64_t vdesc[kKVStages];
-#pragma unroll
-      for (int st = 0; st < kKVStages; ++st) vdesc[st] = make_smem_desc_sw128(smem_u32(sV + st * kVBytes));
+      const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV));
       const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes));
       int vstage = 0;
       uint32_t vphase = 0;
       uint32_t blk = 0;
+      int dn = 0;
       for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
         for (int j = 0; j < num_kv; ++j) {
           const uint32_t par = (blk + j) & 1;
           const uint32_t acc0 = j != 0;          // the first block of an item overwrites O / L
+          const int ksteps = (j == num_kv - 1) ? last_len / 16 : kBKV / 16;
           mbar_wait(&bars->v_full[vstage], vphase);
-          const uint64_t vd = vdesc[vstage];
-          if (j < num_kv - 1 || last_len == kBKV) {
-            uint32_t pending = 3;
-            uint32_t spins = 0;
-            while (pending) {
+          if (lane == 0) dbg_event(dbg, 2, dn, 10 + j);
+          const uint64_t vd = vdesc0 + static_cast<uint64_t>(vstage * (kVBytes / 16));
 #pragma unroll
-              for (int x = 0; x < 2; ++x) {
-                if ((pending >> x) & 1) {
-                  if (mbar_try_wait(&bars->p_full[x], par)) {
-                    tc_fence_after_sync();
+          for (int x = 0; x < 2; ++x) {
+            mbar_wait(&bars->p_full[x], par);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint64_t pbase = pdesc0 + static_cast<uint64_t>(x * (kPBytes / 16));
+              if (ksteps == kBKV / 16) {
 #pragma unroll
-                    for (int k = 0; k < kBKV / 16; ++k) {
-                      const uint64_t pd = pdesc[x] + static_cast<uint64_t>((k >> 2) * (kBQ * 128 / 16) + (k & 3) * 2);
-                      umma_f16_ss(tmem_base + kColPV + x * kHD, pd, vd + k * 128, idesc_pv, acc0 | (k != 0));
-                      umma_f16_ss(tmem_base + kColL + x * 16, pd, odesc + (k & 3) * 2, idesc_l, acc0 | (k != 0));
-                    }
-                    umma_commit(&bars->pv_done[x]);
-                    pending &= ~(1u << x);
-                  }
+                for (int k = 0; k < kBKV / 16; ++k) {
+                  const uint64_t pd = pbase + static_cast<uint64_t>((k >> 2) * (kBQ * 128 / 16) + (k & 3) * 2);
+                  umma_f16_ss(tmem_base + kColPV + x * kHD, pd, vd + k * 128, idesc_pv, acc0 | (k != 0));
+                  umma_f16_ss(tmem_base + kColL + x * 16, pd, odesc + (k & 3) * 2, idesc_l, acc0 | (k != 0));
                 }
-              }
-              if (++spins > (1u << 28)) __trap();
-            }
-          } else {
-            const int ksteps = last_len / 16;
-#pragma unroll
-            for (int x = 0; x < 2; ++x) {
-              mbar_wait(&bars->p_full[x], par);
-              tc_fence_after_sync();
+              } else {
 #pragma unroll 1
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t pd = pdesc[x] + static_cast<uint64_t>((k >> 2) * (kBQ * 128 / 16) + (k & 3) * 2);
-                umma_f16_ss(tmem_base + kColPV + x * kHD, pd, vd + k * 128, idesc_pv, acc0 | (k != 0));
-                umma_f16_ss(tmem_base + kColL + x * 16, pd, odesc + (k & 3) * 2, idesc_l, acc0 | (k != 0));
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t pd = pbase + static_cast<uint64_t>((k >> 2) * (kBQ * 128 / 16) + (k & 3) * 2);
+                  umma_f16_ss(tmem_base + kColPV + x * kHD, pd, vd + k * 128, idesc_pv, acc0 | (k != 0));
+                  umma_f16_ss(tmem_base + kColL + x * 16, pd, odesc + (k & 3) * 2, idesc_l, acc0 | (k != 0));
+                }
               }
               umma_commit(&bars->pv_done[x]);
             }
+            __syncwarp();
+            if (lane == 0) dbg_event(dbg, 2, dn, 40 + 20 * x + j);
           }
-          umma_commit(&bars->v_empty[vstage]);
+          if (elect_one()) umma_commit(&bars->v_empty[vstage]);
+          __syncwarp();
           if (++vstage == kKVStages) { vstage = 0; vphase ^= 1; }
         }
         blk += num_kv;
@@ -425,6 +451,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
     const uint32_t tL = tmem_base + lane_addr + kColL + x * 16;
     uint8_t* prow = sP + x * kPBytes + r * 128;
     uint32_t blk = 0;
+    int dn = 0;
+    const bool dbg_me = (sub == 0 && lane == 0);
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int pair = it % pairs;
       const int head = (it / pairs) % heads;
@@ -436,18 +464,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
         const int valid = N - j * kBKV;            // keys >= valid are out of range
         const int len = (j == num_kv - 1) ? last_len : kBKV;
         mbar_wait(&bars->s_full[x], par);
+        if (dbg_me) dbg_event(dbg, 3 + x, dn, 10 + j);
         tc_fence_after_sync();
         if (len == kBKV && valid >= kBKV) {
-          softmax_block_full(bars, x, lane, tS, tPV, tL, prow, r, j == 0, par, scale_log2e, m_used);
+          softmax_block_full(bars, x, lane, tS, tPV, tL, prow, r, j == 0, par, scale_log2e, m_used, flags);
         } else {
           softmax_block_tail(bars, x, lane, tS, tPV, tL, prow, r, len, valid, j == 0, par, scale_log2e, m_used);
         }
         fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the UMMA
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_full[x]);
+        if (dbg_me) dbg_event(dbg, 3 + x, dn, 30 + j);
       }
       // Drain: O and the row sums are complete once PV of the last block has retired.
       mbar_wait(&bars->pv_done[x], (blk + num_kv - 1) & 1);
+      if (dbg_me) dbg_event(dbg, 3 + x, dn, 90);
       tc_fence_after_sync();
       float o[kHD];
       uint32_t lsum;
@@ -511,7 +542,7 @@ int attention_f16(const __half* qkv, __half* out, int B, int N, int heads, cudaS
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // hd^-0.5 * log2(e), hd = 64
   ProfScope prof(PROF_ATTENTION, stream, 4.0 * B * heads * static_cast<double>(N) * N * kHD);
   attention_kernel<<<grid, kAttnThreads, AttnSmem::total, stream>>>(tm, out, N, D, heads, num_items,
-                                                                    scale_log2e);
+                                                                    scale_log2e, g_attn_flags, g_attn_dbg);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

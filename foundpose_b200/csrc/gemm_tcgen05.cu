@@ -674,7 +674,11 @@ int launch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 
 static bool g_force_1sm = false;
 static int g_tuning_flags = 0;   // spare A/B switches for experiments (GemmParams::flags)
-void gemm_force_1sm(int on) { g_force_1sm = (on & 1) != 0; g_tuning_flags = on >> 1; }
+void gemm_force_1sm(int on) {
+  g_force_1sm = (on & 1) != 0;
+  g_tuning_flags = (on >> 1) & 0xff;
+  attention_set_flags(on >> 16);   // upper half: attention experiment switches
+}
 
 int gemm_pick_bn(int M, int N) {
   if (N % 256 != 0) return 128;

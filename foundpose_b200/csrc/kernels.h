@@ -54,6 +54,8 @@ int final_norm_tokens(const float* x, const float* w, const float* b, float* out
 
 // ---- attention_tcgen05.cu ---------------------------------------------------------------
 int attention_f16(const __half* qkv, __half* out, int B, int N, int heads, cudaStream_t stream);
+void attention_set_flags(int flags);   // experiment switches, 0 in production
+void attention_set_debug_buffer(void* p);   // device buffer of 5 x 2048 u64 timeline events, or NULL
 
 
 // ---- knn_tcgen05.cu ---------------------------------------------------------------------

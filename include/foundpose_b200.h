@@ -47,6 +47,10 @@ int fp_gemm_tn_f16(int epilogue, const void* A, int lda, const void* B, int ldb,
  * kernel (default 0). */
 int fp_gemm_force_1sm(int on);
 
+/* Debug: device buffer of 5 x 2048 uint64 that CTA 0 of the attention kernel fills with
+ * (tag << 48 | globaltimer ns) events per warp role (tools/attn_timeline.py); NULL disables. */
+int fp_attention_debug_buffer(void* device_buffer);
+
 /* Single-tile UMMA descriptor probe used by the GPU tests (not on the hot path). */
 int fp_umma_probe(const void* A, const void* B, float* out, int b_mn_major, void* stream);
 
