@@ -147,77 +147,84 @@ struct AttnBars {
 // P <= 256 stays well inside fp16 and the rescale is rare after the first blocks.
 constexpr float kRescaleThreshold = 8.0f;   // log2 domain
 
-// Shared tail of both block variants: given the block max, decide whether the accumulators must be
-// rescaled (after PV(j-1) retired) and return -m_used * c.
-__device__ __forceinline__ float update_reference_max(AttnBars* bars, int x, uint32_t tPV, uint32_t tL,
-                                                      bool first, uint32_t par, float scale_log2e,
-                                                      float m_blk, float& m_used) {
+// Decide the reference max of this block.  Returns true when the accumulators must be rescaled
+// (by exp2((m_old - m_used) * c)) once PV(j-1) has retired; warp-uniform.
+__device__ __forceinline__ bool choose_reference_max(bool first, float scale_log2e, float m_blk,
+                                                     float& m_used, float& m_old) {
   const float m_new = fmaxf(m_used, m_blk);
+  m_old = m_used;
   if (first) {
     m_used = m_new;
-  } else {
-    // PV(j-1) done: the P buffer may be overwritten and O / L are stable.
-    mbar_wait(&bars->pv_done[x], par ^ 1);
-    tc_fence_after_sync();
-    const bool need = (m_new - m_used) * scale_log2e > kRescaleThreshold;
-    if (__any_sync(0xffffffffu, need)) {
-      rescale_accumulators(tPV, tL, fast_exp2((m_used - m_new) * scale_log2e));
-      m_used = m_new;
-      tc_fence_before_sync();
-    }
+    return false;
   }
-  return -m_used * scale_log2e;
+  const bool need = (m_new - m_used) * scale_log2e > kRescaleThreshold;
+  const bool any = __any_sync(0xffffffffu, need);
+  if (any) m_used = m_new;
+  return any;
 }
 
-__device__ __forceinline__ void store_p8(uint8_t* prow, int r, int c, const uint32_t* s8, float scale_log2e,
-                                         float neg_m, int flags = 0) {
-  uint4 pk;
-  if (flags & 1) {   // experiment: no MUFU
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(fmaf(__uint_as_float(s8[1]), scale_log2e, neg_m)), "f"(fmaf(__uint_as_float(s8[0]), scale_log2e, neg_m)));
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(fmaf(__uint_as_float(s8[3]), scale_log2e, neg_m)), "f"(fmaf(__uint_as_float(s8[2]), scale_log2e, neg_m)));
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk.z) : "f"(fmaf(__uint_as_float(s8[5]), scale_log2e, neg_m)), "f"(fmaf(__uint_as_float(s8[4]), scale_log2e, neg_m)));
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk.w) : "f"(fmaf(__uint_as_float(s8[7]), scale_log2e, neg_m)), "f"(fmaf(__uint_as_float(s8[6]), scale_log2e, neg_m)));
-    const int atom = c >> 3, cc = c & 7;
-    if (!(flags & 2)) *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
-    return;
+// PV(j-1) done: the P buffer may be overwritten and O / L are stable (and can be rescaled).
+__device__ __forceinline__ void wait_prev_pv(AttnBars* bars, int x, uint32_t tPV, uint32_t tL, bool first,
+                                             uint32_t par, bool rescale, float scale_log2e, float m_old,
+                                             float m_used) {
+  if (first) return;
+  mbar_wait(&bars->pv_done[x], par ^ 1);
+  tc_fence_after_sync();
+  if (rescale) {
+    rescale_accumulators(tPV, tL, fast_exp2((m_old - m_used) * scale_log2e));
+    tc_fence_before_sync();
   }
+}
+
+__device__ __forceinline__ uint4 exp_pack8(const uint32_t* s8, float scale_log2e, float neg_m) {
+  uint4 pk;
   pk.x = exp2_f16x2(fmaf(__uint_as_float(s8[0]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[1]), scale_log2e, neg_m));
   pk.y = exp2_f16x2(fmaf(__uint_as_float(s8[2]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[3]), scale_log2e, neg_m));
   pk.z = exp2_f16x2(fmaf(__uint_as_float(s8[4]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[5]), scale_log2e, neg_m));
   pk.w = exp2_f16x2(fmaf(__uint_as_float(s8[6]), scale_log2e, neg_m), fmaf(__uint_as_float(s8[7]), scale_log2e, neg_m));
-  // 128B swizzle: 16-byte chunk index XOR (row % 8); atom = c / 8.
+  return pk;
+}
+
+// 128B swizzle of the P operand: 16-byte chunk index XOR (row % 8); atom = chunk / 8.
+__device__ __forceinline__ void store_p_chunk(uint8_t* prow, int r, int c, const uint4& pk) {
   const int atom = c >> 3, cc = c & 7;
-  if (!(flags & 2)) *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
+  *reinterpret_cast<uint4*>(prow + atom * (kBQ * 128) + ((cc ^ (r & 7)) << 4)) = pk;
 }
 
 // Full block: all 128 keys valid - fully static code, S held in registers (one TMEM pass).
+// The exponentials are computed BEFORE waiting for PV(j-1), so that wait is off the critical path;
+// only the shared-memory stores of P come after it.
 __device__ __forceinline__ void softmax_block_full(AttnBars* bars, int x, int lane, uint32_t tS, uint32_t tPV,
                                                    uint32_t tL, uint8_t* prow, int r, bool first,
-                                                   uint32_t par, float scale_log2e, float& m_used, int flags) {
+                                                   uint32_t par, float scale_log2e, float& m_used,
+                                                   unsigned long long* dbg, int& dn, bool dbg_me, int j) {
   uint32_t s[kBKV];
-  if (flags & 16) {   // experiment: no TMEM read of S
-#pragma unroll
-    for (int i = 0; i < kBKV; ++i) s[i] = 0;
-  } else {
 #pragma unroll
   for (int c = 0; c < kBKV / 32; ++c) {
     uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
     tmem_ld_32x32b_x32(tS + c * 32, chunk);
   }
   tmem_ld_wait();
-  }
   tc_fence_before_sync();
   __syncwarp();
   if (lane == 0) mbar_arrive(&bars->s_empty[x]);   // S may be recomputed for the next block
+  if (dbg_me) dbg_event(dbg, 3 + x, dn, 200 + j);
   float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-  if (!(flags & 4))
 #pragma unroll
   for (int i = 0; i < kBKV; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[i]));
   const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-  const float neg_m = update_reference_max(bars, x, tPV, tL, first, par, scale_log2e, m_blk, m_used);
+  float m_old;
+  const bool rescale = choose_reference_max(first, scale_log2e, m_blk, m_used, m_old);
+  const float neg_m = -m_used * scale_log2e;
+  if (dbg_me) dbg_event(dbg, 3 + x, dn, 300 + j);
+  uint4 pk[kBKV / 8];
 #pragma unroll
-  for (int c = 0; c < kBKV / 8; ++c) store_p8(prow, r, c, &s[c * 8], scale_log2e, neg_m, flags);
+  for (int c = 0; c < kBKV / 8; ++c) pk[c] = exp_pack8(&s[c * 8], scale_log2e, neg_m);
+  if (dbg_me) dbg_event(dbg, 3 + x, dn, 400 + j);
+  wait_prev_pv(bars, x, tPV, tL, first, par, rescale, scale_log2e, m_old, m_used);
+#pragma unroll
+  for (int c = 0; c < kBKV / 8; ++c) store_p_chunk(prow, r, c, pk[c]);
+  if (dbg_me) dbg_event(dbg, 3 + x, dn, 500 + j);
 }
 
 // Last (partial) block: `len` (multiple of 16) columns were computed, keys >= valid are masked.
@@ -237,7 +244,10 @@ __device__ __forceinline__ void softmax_block_tail(AttnBars* bars, int x, int la
     for (int i = 0; i < 32; ++i)
       if (c * 32 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
   }
-  const float neg_m = update_reference_max(bars, x, tPV, tL, first, par, scale_log2e, m_blk, m_used);
+  float m_old;
+  const bool rescale = choose_reference_max(first, scale_log2e, m_blk, m_used, m_old);
+  const float neg_m = -m_used * scale_log2e;
+  wait_prev_pv(bars, x, tPV, tL, first, par, rescale, scale_log2e, m_old, m_used);
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     uint32_t v[32];
@@ -248,7 +258,7 @@ __device__ __forceinline__ void softmax_block_tail(AttnBars* bars, int x, int la
       if (c * 32 + i >= valid) v[i] = 0xff800000u;   // -inf -> P = 0
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-      if (c * 32 + g * 8 < len) store_p8(prow, r, c * 4 + g, &v[g * 8], scale_log2e, neg_m);
+      if (c * 32 + g * 8 < len) store_p_chunk(prow, r, c * 4 + g, exp_pack8(&v[g * 8], scale_log2e, neg_m));
   }
   tc_fence_before_sync();
   __syncwarp();
@@ -467,7 +477,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
         if (dbg_me) dbg_event(dbg, 3 + x, dn, 10 + j);
         tc_fence_after_sync();
         if (len == kBKV && valid >= kBKV) {
-          softmax_block_full(bars, x, lane, tS, tPV, tL, prow, r, j == 0, par, scale_log2e, m_used, flags);
+          softmax_block_full(bars, x, lane, tS, tPV, tL, prow, r, j == 0, par, scale_log2e, m_used, dbg, dn, dbg_me, j);
         } else {
           softmax_block_tail(bars, x, lane, tS, tPV, tL, prow, r, len, valid, j == 0, par, scale_log2e, m_used);
         }
