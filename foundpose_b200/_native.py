@@ -198,6 +198,17 @@ def knn_items_dense(items: torch.Tensor, q_total: int, b_row0: int, b_rows: int)
     call("fp_knn_items_dense", ptr(items), _i(q_total), _i(b_row0), _i(b_rows), stream_ptr(items.device))
 
 
+def knn_items_split(items: torch.Tensor, q_total: int, b_row0: int, b_rows: int, num_chunks: int, chunk_rows: int) -> None:
+    call("fp_knn_items_split", ptr(items), _i(q_total), _i(b_row0), _i(b_rows), _i(num_chunks), _i(chunk_rows),
+         stream_ptr(items.device))
+
+
+def knn_merge(part_d, part_i, num_chunks: int, q_pad: int, nq: int, k: int, chunk_rows: int, b_rows: int,
+              descending: bool, out_d, out_i) -> None:
+    call("fp_knn_merge", ptr(part_d), ptr(part_i), _i(num_chunks), _i(q_pad), _i(nq), _i(k), _i(chunk_rows),
+         _i(b_rows), _i(int(descending)), ptr(out_d), ptr(out_i), stream_ptr(part_d.device))
+
+
 def knn_search_items(q16, q_sqnorm, bank16, bank_sqnorm, items, num_items, metric: int, k: int, out_d, out_i) -> None:
     require_cuda(q16, "q16", torch.float16)
     require_cuda(bank16, "bank16", torch.float16)

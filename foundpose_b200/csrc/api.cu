@@ -193,6 +193,18 @@ int fp_knn_items_dense(fp_knn_item* items, int q_total, int b_row0, int b_rows, 
                                    static_cast<cudaStream_t>(stream));
 }
 
+int fp_knn_items_split(fp_knn_item* items, int q_total, int b_row0, int b_rows, int num_chunks,
+                       int chunk_rows, void* stream) {
+  return fp::knn_build_items_split(reinterpret_cast<fp::KnnItem*>(items), q_total, b_row0, b_rows, num_chunks,
+                                   chunk_rows, static_cast<cudaStream_t>(stream));
+}
+
+int fp_knn_merge(const float* part_d, const int64_t* part_i, int num_chunks, int q_pad, int nq, int k,
+                 int chunk_rows, int b_rows, int descending, float* out_d, int64_t* out_i, void* stream) {
+  return fp::knn_merge(part_d, part_i, num_chunks, q_pad, nq, k, chunk_rows, b_rows, descending, out_d, out_i,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_sqnorm,
                         const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
                         int dim, const fp_knn_item* items, int num_items, int metric, int k,

@@ -72,6 +72,10 @@ struct KnnItem {
 };
 int knn_items_per_rows(int rows);
 int knn_build_items_dense(KnnItem* items, int q_total, int b_row0, int b_rows, cudaStream_t stream);
+int knn_build_items_split(KnnItem* items, int q_total, int b_row0, int b_rows, int num_chunks,
+                          int chunk_rows, cudaStream_t stream);
+int knn_merge(const float* part_d, const int64_t* part_i, int num_chunks, int q_pad, int nq, int k,
+              int chunk_rows, int b_rows, int descending, float* out_d, int64_t* out_i, cudaStream_t stream);
 int row_sqnorm_f16(const __half* x, float* out, long rows, int dim, cudaStream_t stream);
 int convert_rows_f16(const float* x, __half* y, long rows, int dim, int l2_normalize,
                      cudaStream_t stream);

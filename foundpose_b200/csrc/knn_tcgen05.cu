@@ -382,9 +382,78 @@ __global__ void build_items_dense_kernel(KnnItem* items, int num_items, int q_to
   }
 }
 
+// Items for a bank split into chunks (few queries, large bank: every SM streams its own slice of
+// the bank so the search is HBM-bound instead of running on one CTA per query block).
+__global__ void build_items_split_kernel(KnnItem* items, int q_blocks, int num_chunks, int q_total,
+                                         int b_row0, int b_rows, int chunk_rows) {
+  const int n = q_blocks * num_chunks;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i / q_blocks, m = i - c * q_blocks;
+    KnnItem it;
+    it.q_row0 = m * BQ;
+    it.q_rows = min(BQ, q_total - m * BQ);
+    it.b_row0 = b_row0 + c * chunk_rows;
+    it.b_rows = max(0, min(chunk_rows, b_rows - c * chunk_rows));
+    it.out_row0 = static_cast<long long>(c) * q_blocks * BQ + m * BQ;
+    it.pad = 0;
+    items[i] = it;
+  }
+}
+
+// Merge per-chunk top-k lists: part_* [num_chunks, q_pad, k] (indices relative to the chunk) ->
+// out_* [nq, k], ordered by (distance, global index).  One thread per query.
+template <int K>
+__global__ void knn_merge_kernel(const float* __restrict__ part_d, const int64_t* __restrict__ part_i,
+                                 int num_chunks, int q_pad, int nq, int k, int chunk_rows, int b_rows,
+                                 int descending, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  TopK<K> best;
+  best.init();
+  for (int c = 0; c < num_chunks; ++c) {
+    if (c * chunk_rows >= b_rows) break;
+    const long base = (static_cast<long>(c) * q_pad + q) * k;
+    for (int j = 0; j < k; ++j) {
+      const long li = part_i[base + j];
+      if (li < 0) continue;
+      const float d = part_d[base + j];
+      best.push_lex(descending ? -d : d, static_cast<int>(c * chunk_rows + li));
+    }
+  }
+  for (int j = 0; j < k; ++j) {
+    const bool ok = best.i[j] >= 0;
+    out_d[static_cast<long>(q) * k + j] = ok ? (descending ? -best.d[j] : best.d[j]) : (descending ? -INFINITY : INFINITY);
+    out_i[static_cast<long>(q) * k + j] = best.i[j];
+  }
+}
+
 }  // namespace
 
 int knn_items_per_rows(int rows) { return (rows + BQ - 1) / BQ; }
+
+int knn_build_items_split(KnnItem* items, int q_total, int b_row0, int b_rows, int num_chunks,
+                          int chunk_rows, cudaStream_t stream) {
+  const int q_blocks = knn_items_per_rows(q_total);
+  const int n = q_blocks * num_chunks;
+  if (n == 0) return 0;
+  FP_REQUIRE(chunk_rows % BX == 0, "knn: chunk_rows=%d must be a multiple of %d", chunk_rows, BX);
+  ProfScope prof(PROF_RETRIEVAL, stream, n * 32.0);
+  build_items_split_kernel<<<(n + 255) / 256, 256, 0, stream>>>(items, q_blocks, num_chunks, q_total, b_row0,
+                                                               b_rows, chunk_rows);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int knn_merge(const float* part_d, const int64_t* part_i, int num_chunks, int q_pad, int nq, int k,
+              int chunk_rows, int b_rows, int descending, float* out_d, int64_t* out_i, cudaStream_t stream) {
+  FP_REQUIRE(k >= 1 && k <= 16, "knn_merge: k=%d is outside [1,16]", k);
+  if (nq <= 0) return 0;
+  ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(num_chunks) * nq * k * 12);
+  knn_merge_kernel<16><<<(nq + 127) / 128, 128, 0, stream>>>(part_d, part_i, num_chunks, q_pad, nq, k, chunk_rows,
+                                                             b_rows, descending, out_d, out_i);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int knn_build_items_dense(KnnItem* items, int q_total, int b_row0, int b_rows, cudaStream_t stream) {
   const int n = knn_items_per_rows(q_total);

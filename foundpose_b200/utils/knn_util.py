@@ -15,6 +15,9 @@ import torch
 from foundpose_b200 import _native
 
 _MAX_K = 16
+_SPLIT_BELOW_ITEMS = 74     # fewer query blocks than half the SMs -> split the bank
+_SPLIT_MIN_ROWS = 16384
+_TARGET_ITEMS = 592         # 148 SMs x 4 items
 
 
 def _device_for(t: torch.Tensor) -> torch.device:
@@ -83,11 +86,29 @@ class KNN:
             cosine = self.metric == "cosine"
             q16 = _native.convert_rows_f16(q, l2_normalize=cosine)
             qn = _native.row_sqnorm_f16(q16)
-            n_items = _native.knn_num_items(nq)
-            items = _native.new_knn_items(n_items, dev)
-            _native.knn_items_dense(items, nq, 0, self._bank16.shape[0])
-            _native.knn_search_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_items,
-                                     1 if cosine else 0, self.k, dist, idx)
+            n_q = _native.knn_num_items(nq)
+            nb = self._bank16.shape[0]
+            metric = 1 if cosine else 0
+            # Few query blocks against a large bank: split the bank so that all SMs stream it.
+            num_chunks = 1
+            if n_q < _SPLIT_BELOW_ITEMS and nb >= _SPLIT_MIN_ROWS:
+                want = max(1, _TARGET_ITEMS // n_q)
+                chunk_rows = max(256, ((nb + want - 1) // want + 255) // 256 * 256)
+                num_chunks = (nb + chunk_rows - 1) // chunk_rows
+            if num_chunks > 1:
+                q_pad = n_q * 128
+                items = _native.new_knn_items(n_q * num_chunks, dev)
+                _native.knn_items_split(items, nq, 0, nb, num_chunks, chunk_rows)
+                part_d = torch.empty((num_chunks * q_pad, self.k), dtype=torch.float32, device=dev)
+                part_i = torch.full((num_chunks * q_pad, self.k), -1, dtype=torch.int64, device=dev)
+                _native.knn_search_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_q * num_chunks,
+                                         metric, self.k, part_d, part_i)
+                _native.knn_merge(part_d, part_i, num_chunks, q_pad, nq, self.k, chunk_rows, nb, cosine, dist, idx)
+            else:
+                items = _native.new_knn_items(n_q, dev)
+                _native.knn_items_dense(items, nq, 0, nb)
+                _native.knn_search_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_q, metric, self.k,
+                                         dist, idx)
             if cosine:
                 dist = 1.0 - dist  # cosine similarity -> cosine distance (reference :98)
         return dist.to(out_device), idx.to(out_device)

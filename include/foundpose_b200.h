@@ -148,6 +148,15 @@ typedef struct {
 int fp_knn_num_items(int q_rows);
 /* Fills items[0 .. fp_knn_num_items(q_total)) for "all query rows vs bank rows [b_row0, +b_rows)". */
 int fp_knn_items_dense(fp_knn_item* items, int q_total, int b_row0, int b_rows, void* stream);
+/* Few queries vs a large bank: split the bank into num_chunks slices of chunk_rows rows
+ * (chunk_rows % 256 == 0) so that every SM streams its own slice (HBM-bound search).  Fills
+ * fp_knn_num_items(q_total) * num_chunks items; chunk c writes its partial top-k lists to output rows
+ * [c * q_pad, c * q_pad + q_total), q_pad = fp_knn_num_items(q_total) * 128.  fp_knn_merge reduces
+ * the partial lists [num_chunks, q_pad, k] to the final [nq, k] ordered by (distance, index). */
+int fp_knn_items_split(fp_knn_item* items, int q_total, int b_row0, int b_rows, int num_chunks,
+                       int chunk_rows, void* stream);
+int fp_knn_merge(const float* part_d, const int64_t* part_i, int num_chunks, int q_pad, int nq, int k,
+                 int chunk_rows, int b_rows, int descending, float* out_d, int64_t* out_i, void* stream);
 /* metric 0: squared L2, ascending (out_d = max(||q||^2 + ||x||^2 - 2<q,x>, 0));
  * metric 1: inner product, descending (out_d = <q,x>).  k <= 16, dim % 64 == 0.
  * q_sqnorm / bank_sqnorm: fp_row_sqnorm_f16 of the respective rows (unused for metric 1).

@@ -68,7 +68,8 @@ def test_pca_vs_golden(gold):
 
 
 @pytest.mark.parametrize("nq,nb,dim,k", [(150, 32, 64, 3), (1000, 2048, 256, 3), (900, 1024, 384, 1),
-                                         (37, 5000, 128, 5), (129, 129, 64, 8), (5, 3, 64, 1)])
+                                         (37, 5000, 128, 5), (129, 129, 64, 8), (5, 3, 64, 1),
+                                         (100, 40000, 128, 5), (300, 70001, 64, 1)])   # last two: split-bank path
 def test_knn_l2_vs_oracle(nq, nb, dim, k):
     from foundpose_b200.utils import knn_util
     from oracle import knn as oknn
