@@ -68,11 +68,13 @@ __global__ void init_special_tokens_kernel(float* __restrict__ x, const float* _
 }
 
 // LayerNorm over D (multiple of 128, <= 2048): one warp per row, row cached in registers.
-template <int MAX_VEC>
+// MAX_VEC float4 per lane; with kExact the row has exactly MAX_VEC * 128 elements (no predicates,
+// registers sized to the row), otherwise D / 128 <= MAX_VEC vectors are used.
+template <int MAX_VEC, bool kExact = false>
 __device__ __forceinline__ void ln_row(const float* __restrict__ xr, int D, const float* __restrict__ w,
                                        const float* __restrict__ bvec, float eps, int lane,
                                        float4 (&v)[MAX_VEC], int& nvec) {
-  nvec = D / 128;
+  nvec = kExact ? MAX_VEC : D / 128;
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i) {
@@ -104,6 +106,7 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ xr, int D, cons
   }
 }
 
+template <int NVEC, bool kExact>
 __global__ void __launch_bounds__(256)
 layernorm_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, const float* __restrict__ w,
                      const float* __restrict__ b, int M, int D, float eps) {
@@ -111,12 +114,12 @@ layernorm_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, const 
   const int warps_per_block = blockDim.x >> 5;
   for (long row = blockIdx.x * static_cast<long>(warps_per_block) + (threadIdx.x >> 5); row < M;
        row += static_cast<long>(gridDim.x) * warps_per_block) {
-    float4 v[16];
+    float4 v[NVEC];
     int nvec;
-    ln_row<16>(x + row * D, D, w, b, eps, lane, v, nvec);
+    ln_row<NVEC, kExact>(x + row * D, D, w, b, eps, lane, v, nvec);
     __half* yr = y + row * D;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < NVEC; ++i) {
       if (i < nvec) {
         __half2 h0 = __floats2half2_rn(v[i].x, v[i].y);
         __half2 h1 = __floats2half2_rn(v[i].z, v[i].w);
@@ -212,7 +215,13 @@ int layernorm_f16(const float* x, __half* y, const float* w, const float* b, int
   FP_REQUIRE(D % 128 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 128 and <= 2048", D);
   ProfScope prof(PROF_LAYERNORM, stream, static_cast<double>(M) * D * 6);
   // Persistent grid (a one-block-per-8-rows launch was measured 20% slower on B200).
-  layernorm_f16_kernel<<<grid_for(M, 8), 256, 0, stream>>>(x, y, w, b, M, D, eps);
+  const int grid = grid_for(M, 8);
+  switch (D / 128) {   // registers sized to the row for the ViT widths
+    case 3: layernorm_f16_kernel<3, true><<<grid, 256, 0, stream>>>(x, y, w, b, M, D, eps); break;
+    case 6: layernorm_f16_kernel<6, true><<<grid, 256, 0, stream>>>(x, y, w, b, M, D, eps); break;
+    case 8: layernorm_f16_kernel<8, true><<<grid, 256, 0, stream>>>(x, y, w, b, M, D, eps); break;
+    default: layernorm_f16_kernel<16, false><<<grid, 256, 0, stream>>>(x, y, w, b, M, D, eps); break;
+  }
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
