@@ -540,11 +540,10 @@ int attention_f16(const __half* qkv, __half* out, int B, int N, int heads, cudaS
   CUtensorMap tm;
   // One descriptor over the whole [B*N, 3D] matrix; box = 128 rows x 64 columns (one head slice).
   if (make_tma_2d_f16(&tm, qkv, static_cast<uint64_t>(B) * N, 3ull * D, 3ull * D, kBQ) != 0) return 3;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (per_device_once(configured)) {
     FP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        AttnSmem::total));
-    configured = true;
   }
   const int pairs = (N + 2 * kBQ - 1) / (2 * kBQ);
   const int num_items = pairs * heads * B;

@@ -286,4 +286,15 @@ int make_tma_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 int make_tma_2d_f32_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                           uint32_t box_rows);
 
+// True the first time it is called for (flag array, current device): kernel attributes such as
+// cudaFuncAttributeMaxDynamicSharedMemorySize are per device, so "configured once" must be too.
+inline bool per_device_once(bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 }  // namespace fp

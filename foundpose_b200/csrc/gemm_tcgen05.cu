@@ -630,11 +630,10 @@ int launch_2sm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
                "gemm_tn: fp16 output must be 16-byte aligned with ld %% 8 == 0");
     if (make_tma_2d_f16(&tmC, p.out_f16, p.M, p.N, p.ld_f16, 32, 64) != 0) return 3;
   }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (per_device_once(configured)) {
     FP_CUDA_CHECK(cudaFuncSetAttribute(gemm2_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
-    configured = true;
   }
   const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / Cfg::BN);
   int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
@@ -648,12 +647,11 @@ template <int BN, int EPI>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (per_device_once(configured)) {
     FP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
-    configured = true;
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;

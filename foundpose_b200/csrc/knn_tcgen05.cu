@@ -312,11 +312,10 @@ template <int K>
 int launch_knn(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* items, int num_items,
                int dim, const float* qnorm, const float* xnorm, int metric_ip, int k_out,
                float* out_d, int64_t* out_i, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (per_device_once(configured)) {
     FP_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kKnnSmem));
-    configured = true;
   }
   const int grid = num_items < kNumSMs ? num_items : kNumSMs;
   ProfScope prof(PROF_KNN, stream, 0.0);

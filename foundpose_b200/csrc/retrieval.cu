@@ -342,11 +342,10 @@ int tfidf_histogram(const int64_t* word_ids, const float* word_dists, int k, con
                     int sqrt_input, float* out, cudaStream_t stream) {
   FP_REQUIRE(W * 4 <= 200 * 1024, "tfidf: %d visual words do not fit in shared memory", W);
   if (B <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (per_device_once(configured)) {
     FP_CUDA_CHECK(cudaFuncSetAttribute(tfidf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        200 * 1024));
-    configured = true;
   }
   ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(B) * W * 4);
   tfidf_kernel<<<B, 256, W * 4, stream>>>(word_ids, word_dists, k, row_start, row_count, idf, W, soft,
