@@ -351,10 +351,18 @@ def run_cuda_arm(args) -> None:
     ln_gbs = ln["work_per_step"] / (ln["ms_per_step"] * 1e-3) / 1e9 if ln["ms_per_step"] > 0 else 0.0
     vit_flops = vit_flops_per_crop(arch, layer) * B
     vit_ms = sum(fam[k]["ms_per_step"] for k in ("gemm", "attention", "layernorm", "vit_misc"))
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            traffic = json.load(f)["avg_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
         "kernel": "gemm_tn_kernel (tcgen05 GEMM, all ViT linear layers + patch embed + PCA)",
         "bound": "tensor", "achieved": gemm_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
-        "frac": gemm_tflops / tensor_peak, "traffic": None, "peak_source": peak_src,
+        "frac": gemm_tflops / tensor_peak, "traffic": traffic,
+        "traffic_note": "avg DRAM read+write bytes per gemm launch (ncu, profiles/r01_gemm_traffic.json)",
+        "peak_source": peak_src,
         "launches_per_step": g["launches_per_step"], "avg_launch_ms": g["ms_per_step"] / max(g["launches_per_step"], 1),
         "share_of_step": g["ms_per_step"] / fam_ms if fam_ms > 0 else None,
         "vit_stage": {"tflops": vit_flops / (vit_ms * 1e-3) / 1e12 if vit_ms > 0 else 0.0,
