@@ -277,12 +277,25 @@ def build_pair_items(top_ids, topn, tpl_off, q_start, q_count, max_q, max_p, ite
          _i(max_q), _i(max_p), ptr(items_q2o), ptr(items_o2q), stream_ptr(top_ids.device))
 
 
+def cyclic_buddies_workspace(num_pairs: int, max_q: int, top_k: int, device) -> Optional[torch.Tensor]:
+    lib = load()
+    lib.fp_cyclic_buddies_workspace_bytes.restype = ctypes.c_uint64
+    nbytes = int(lib.fp_cyclic_buddies_workspace_bytes(_i(num_pairs), _i(max_q), _i(top_k)))
+    if nbytes == 0:
+        return None
+    return torch.empty(((nbytes + 7) // 8,), dtype=torch.int64, device=device)
+
+
 def cyclic_buddies(points, q_start, q_count, q2o, o2q, top_ids, topn, tpl_off, feat_perm, vertices, max_q, max_p,
-                   top_k, out_qids, out_vids, out_dists, out_scores, out_c2d, out_c3d, out_count) -> None:
+                   top_k, out_qids, out_vids, out_dists, out_scores, out_c2d, out_c3d, out_count,
+                   workspace: Optional[torch.Tensor] = None) -> None:
+    if workspace is None:
+        workspace = cyclic_buddies_workspace(top_ids.numel(), max_q, top_k, points.device)
+    ws_bytes = workspace.numel() * 8 if workspace is not None else 0
     call("fp_cyclic_buddies", ptr(points), ptr(q_start), ptr(q_count), ptr(q2o), ptr(o2q), ptr(top_ids),
          _i(top_ids.numel()), _i(topn), ptr(tpl_off), ptr(feat_perm), ptr(vertices), _i(max_q), _i(max_p), _i(top_k),
          ptr(out_qids), ptr(out_vids), ptr(out_dists), ptr(out_scores), ptr(out_c2d), ptr(out_c3d), ptr(out_count),
-         stream_ptr(points.device))
+         ptr(workspace), ctypes.c_uint64(ws_bytes), stream_ptr(points.device))
 
 
 # ---- ViT handle ---------------------------------------------------------------------------------

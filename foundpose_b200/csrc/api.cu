@@ -271,11 +271,16 @@ int fp_cyclic_buddies(const float* points, const int32_t* q_start, const int32_t
                       int num_pairs, int topn, const int32_t* tpl_off, const int64_t* feat_perm,
                       const float* vertices, int max_q, int max_p, int top_k, int64_t* out_query_ids,
                       int64_t* out_vertex_ids, float* out_dists, float* out_scores,
-                      float* out_coord_2d, float* out_coord_3d, int32_t* out_count, void* stream) {
+                      float* out_coord_2d, float* out_coord_3d, int32_t* out_count, void* workspace,
+                      uint64_t workspace_bytes, void* stream) {
   return fp::cyclic_buddies(points, q_start, q_count, q2o, o2q, top_ids, num_pairs, topn, tpl_off,
                             feat_perm, vertices, max_q, max_p, top_k, out_query_ids, out_vertex_ids,
-                            out_dists, out_scores, out_coord_2d, out_coord_3d, out_count,
-                            static_cast<cudaStream_t>(stream));
+                            out_dists, out_scores, out_coord_2d, out_coord_3d, out_count, workspace,
+                            static_cast<size_t>(workspace_bytes), static_cast<cudaStream_t>(stream));
+}
+
+uint64_t fp_cyclic_buddies_workspace_bytes(int num_pairs, int max_q, int top_k) {
+  return fp::cyclic_buddies_workspace_bytes(num_pairs, max_q, top_k);
 }
 
 }  // extern "C"

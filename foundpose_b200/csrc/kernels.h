@@ -108,7 +108,8 @@ int cyclic_buddies(const float* points, const int* q_start, const int* q_count, 
                    const int64_t* o2q, const int64_t* top_ids, int num_pairs, int topn,
                    const int* tpl_off, const int64_t* feat_perm, const float* vertices, int max_q,
                    int max_p, int top_k, int64_t* out_qids, int64_t* out_vids, float* out_dists,
-                   float* out_scores, float* out_c2d, float* out_c3d, int* out_count,
-                   cudaStream_t stream);
+                   float* out_scores, float* out_c2d, float* out_c3d, int* out_count, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+size_t cyclic_buddies_workspace_bytes(int num_pairs, int max_q, int top_k);
 
 }  // namespace fp

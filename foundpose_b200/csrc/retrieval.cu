@@ -265,6 +265,64 @@ __global__ void build_pair_items_kernel(const int64_t* __restrict__ top_ids, int
 // ---------------------------------------------------------------------------------------
 constexpr int kCycMax = 4096;
 
+// 64-bit sort key of query i: (cycle distance bits << 32) | i.  The distance is non-negative so its
+// bit pattern is monotonic; ties order by query id (canonical rule).
+__device__ __forceinline__ unsigned long long cycle_key(const float* __restrict__ points, int qs,
+                                                        const int64_t* __restrict__ q2o_p,
+                                                        const int64_t* __restrict__ o2q_p, int i) {
+  const long o = q2o_p[i];
+  const long c = o2q_p[o];
+  const float dx = points[(qs + i) * 2] - points[(qs + c) * 2];
+  const float dy = points[(qs + i) * 2 + 1] - points[(qs + c) * 2 + 1];
+  // torch.linalg.norm over 2 components: sqrt(dx^2 + dy^2).
+  const float d = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+  return (static_cast<unsigned long long>(__float_as_uint(d)) << 32) | static_cast<unsigned>(i);
+}
+
+// Pre-selection for more than kCycMax keys per pair: each CTA sorts one chunk of kCycMax keys
+// (level 0: computed from the cycle distances; later levels: read from `in`) and keeps its `keep`
+// smallest.  out: [pairs, chunks * keep], padded with ~0.
+__global__ void __launch_bounds__(512)
+cyclic_preselect_kernel(const float* __restrict__ points, const int* __restrict__ q_start,
+                        const int* __restrict__ q_count, const int64_t* __restrict__ q2o,
+                        const int64_t* __restrict__ o2q, const int64_t* __restrict__ top_ids, int topn,
+                        int max_q, int max_p, const unsigned long long* __restrict__ in, int n_in, int keep,
+                        unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long keys[kCycMax];
+  const int chunk = blockIdx.x, pair = blockIdx.y, chunks = gridDim.x;
+  const int b = pair / topn;
+  const int n = q_count[b];
+  const int qs = q_start[b];
+  const bool ok = top_ids[pair] >= 0;
+  const int64_t* q2o_p = q2o + static_cast<long>(pair) * max_q;
+  const int64_t* o2q_p = o2q + static_cast<long>(pair) * max_p;
+  for (int i = threadIdx.x; i < kCycMax; i += blockDim.x) {
+    const int g = chunk * kCycMax + i;
+    unsigned long long key = ~0ull;
+    if (in) {
+      if (g < n_in) key = in[static_cast<long>(pair) * n_in + g];
+    } else if (ok && g < n) {
+      key = cycle_key(points, qs, q2o_p, o2q_p, g);
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= kCycMax; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < kCycMax / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = keys[lo], c = keys[hi];
+        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < keep; j += blockDim.x)
+    out[(static_cast<long>(pair) * chunks + chunk) * keep + j] = keys[j];
+}
+
 __global__ void __launch_bounds__(512)
 cyclic_buddies_kernel(const float* __restrict__ points, const int* __restrict__ q_start,
                       const int* __restrict__ q_count, const int64_t* __restrict__ q2o,
@@ -274,8 +332,8 @@ cyclic_buddies_kernel(const float* __restrict__ points, const int* __restrict__ 
                       int64_t* __restrict__ out_qids, int64_t* __restrict__ out_vids,
                       float* __restrict__ out_dists, float* __restrict__ out_scores,
                       float* __restrict__ out_c2d, float* __restrict__ out_c3d,
-                      int* __restrict__ out_count) {
-  extern __shared__ unsigned long long keys[];  // next pow2 >= n
+                      int* __restrict__ out_count, const unsigned long long* __restrict__ cand, int n_cand) {
+  extern __shared__ unsigned long long keys[];  // next pow2 >= number of keys sorted here
   const int pair = blockIdx.x;
   const int b = pair / topn;
   const int n = q_count[b];
@@ -287,18 +345,17 @@ cyclic_buddies_kernel(const float* __restrict__ points, const int* __restrict__ 
   const int ts = tpl_off[t];
   const int64_t* q2o_p = q2o + static_cast<long>(pair) * max_q;
   const int64_t* o2q_p = o2q + static_cast<long>(pair) * max_p;
+  // Keys come either straight from the cycle distances (n <= kCycMax) or from the candidate list
+  // produced by the pre-selection passes (large query sets, e.g. grid_cell_size = 1).
+  const int n_keys = cand ? n_cand : n;
   int npow = 1;
-  while (npow < n) npow <<= 1;
+  while (npow < n_keys) npow <<= 1;
   for (int i = threadIdx.x; i < npow; i += blockDim.x) {
     unsigned long long key = ~0ull;
-    if (i < n) {
-      const long o = q2o_p[i];
-      const long c = o2q_p[o];
-      const float dx = points[(qs + i) * 2] - points[(qs + c) * 2];
-      const float dy = points[(qs + i) * 2 + 1] - points[(qs + c) * 2 + 1];
-      // torch.linalg.norm over 2 components: sqrt(dx^2 + dy^2), non-negative -> bits are monotonic.
-      const float d = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-      key = (static_cast<unsigned long long>(__float_as_uint(d)) << 32) | static_cast<unsigned>(i);
+    if (cand) {
+      if (i < n_cand) key = cand[static_cast<long>(pair) * n_cand + i];
+    } else if (i < n) {
+      key = cycle_key(points, qs, q2o_p, o2q_p, i);
     }
     keys[i] = key;
   }
@@ -397,22 +454,57 @@ int build_pair_items(const int64_t* top_ids, int num_pairs, int topn, const int*
   return 0;
 }
 
+size_t cyclic_buddies_workspace_bytes(int num_pairs, int max_q, int top_k) {
+  if (max_q <= kCycMax) return 0;
+  const int keep = top_k < kCycMax ? top_k : kCycMax;
+  const size_t chunks0 = (max_q + kCycMax - 1) / kCycMax;
+  // two ping-pong candidate buffers, the first level is the largest
+  return 2 * static_cast<size_t>(num_pairs) * chunks0 * keep * sizeof(unsigned long long);
+}
+
 int cyclic_buddies(const float* points, const int* q_start, const int* q_count, const int64_t* q2o,
                    const int64_t* o2q, const int64_t* top_ids, int num_pairs, int topn,
                    const int* tpl_off, const int64_t* feat_perm, const float* vertices, int max_q,
                    int max_p, int top_k, int64_t* out_qids, int64_t* out_vids, float* out_dists,
-                   float* out_scores, float* out_c2d, float* out_c3d, int* out_count,
-                   cudaStream_t stream) {
-  FP_REQUIRE(max_q <= kCycMax,
-             "cyclic_buddies: %d query points per crop exceed the supported maximum of %d", max_q,
-             kCycMax);
+                   float* out_scores, float* out_c2d, float* out_c3d, int* out_count, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream) {
   if (num_pairs <= 0) return 0;
+  FP_REQUIRE(top_k >= 1, "cyclic_buddies: top_k must be positive");
+  const unsigned long long* cand = nullptr;
+  int n_cand = 0;
+  if (max_q > kCycMax) {
+    // Large query sets (e.g. the reference's default grid_cell_size = 1 -> 176 400 points): reduce to
+    // <= kCycMax candidates with chunk-wise pre-selection passes, then run the final sort.
+    FP_REQUIRE(top_k <= kCycMax, "cyclic_buddies: top_k=%d exceeds %d", top_k, kCycMax);
+    const size_t need = cyclic_buddies_workspace_bytes(num_pairs, max_q, top_k);
+    FP_REQUIRE(workspace != nullptr && workspace_bytes >= need,
+               "cyclic_buddies: %d query points per crop need a workspace of %zu bytes", max_q, need);
+    unsigned long long* buf0 = static_cast<unsigned long long*>(workspace);
+    unsigned long long* buf1 = buf0 + need / (2 * sizeof(unsigned long long));
+    const unsigned long long* in = nullptr;
+    int n_in = max_q;
+    unsigned long long* out = buf0;
+    while (n_in > kCycMax) {
+      const int chunks = (n_in + kCycMax - 1) / kCycMax;
+      dim3 grid(chunks, num_pairs);
+      ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(num_pairs) * n_in * 8);
+      cyclic_preselect_kernel<<<grid, 512, 0, stream>>>(points, q_start, q_count, q2o, o2q, top_ids, topn, max_q,
+                                                        max_p, in, n_in, top_k, out);
+      FP_CUDA_CHECK(cudaGetLastError());
+      in = out;
+      n_in = chunks * top_k;
+      out = (out == buf0) ? buf1 : buf0;
+    }
+    cand = in;
+    n_cand = n_in;
+  }
   int npow = 1;
-  while (npow < max_q) npow <<= 1;
+  const int n_sort = cand ? n_cand : max_q;
+  while (npow < n_sort) npow <<= 1;
   ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(num_pairs) * (max_q + max_p) * 8);
   cyclic_buddies_kernel<<<num_pairs, 512, npow * 8, stream>>>(
       points, q_start, q_count, q2o, o2q, top_ids, topn, tpl_off, feat_perm, vertices, max_q, max_p,
-      top_k, out_qids, out_vids, out_dists, out_scores, out_c2d, out_c3d, out_count);
+      top_k, out_qids, out_vids, out_dists, out_scores, out_c2d, out_c3d, out_count, cand, n_cand);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

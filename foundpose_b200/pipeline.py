@@ -157,6 +157,7 @@ class RetrievalEngine:
         self.o2q_d = torch.empty((npairs * self.max_p, 1), dtype=f32, device=dev)
         self.o2q_i = torch.zeros((npairs * self.max_p, 1), dtype=i64, device=dev)
         k = top_k_buddies
+        self.cyc_workspace = _native.cyclic_buddies_workspace(npairs, stride, top_k_buddies, dev)
         self.out = MatchOutputs(
             template_ids=self.top_ids, template_scores=self.top_scores,
             count=torch.zeros((batch, self.topn), dtype=i32, device=dev),
@@ -192,7 +193,8 @@ class RetrievalEngine:
         o = self.out
         _native.cyclic_buddies(points, self.q_start, q_count, self.q2o_i, self.o2q_i, self.top_ids, self.topn,
                                ix.tpl_off, ix.feat_perm, ix.vertices, self.stride, self.max_p, self.top_k,
-                               o.query_ids, o.vertex_ids, o.dists, o.scores, o.coord_2d, o.coord_3d, o.count)
+                               o.query_ids, o.vertex_ids, o.dists, o.scores, o.coord_2d, o.coord_3d, o.count,
+                               self.cyc_workspace)
         return o
 
 

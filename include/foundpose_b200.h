@@ -212,13 +212,17 @@ int fp_build_pair_items(const int64_t* top_ids, int num_pairs, int topn, const i
 /* cyclic_buddies_matching + the gathers of establish_correspondences
  * (utils/corresp_util.py:50-68, 135-155) for every pair; outputs have top_k rows per pair, the
  * first out_count[p] = min(top_k, q_count[b]) are valid, ordered by (cycle distance, query id).
- * feat_perm (int64, may be NULL) maps sorted bank rows back to original feature ids. */
+ * feat_perm (int64, may be NULL) maps sorted bank rows back to original feature ids.
+ * More than 4096 query points per crop (e.g. the reference default grid_cell_size = 1) need a scratch
+ * buffer of fp_cyclic_buddies_workspace_bytes() bytes; otherwise workspace may be NULL. */
 int fp_cyclic_buddies(const float* points, const int32_t* q_start, const int32_t* q_count,
                       const int64_t* q2o, const int64_t* o2q, const int64_t* top_ids,
                       int num_pairs, int topn, const int32_t* tpl_off, const int64_t* feat_perm,
                       const float* vertices, int max_q, int max_p, int top_k, int64_t* out_query_ids,
                       int64_t* out_vertex_ids, float* out_dists, float* out_scores,
-                      float* out_coord_2d, float* out_coord_3d, int32_t* out_count, void* stream);
+                      float* out_coord_2d, float* out_coord_3d, int32_t* out_count, void* workspace,
+                      uint64_t workspace_bytes, void* stream);
+uint64_t fp_cyclic_buddies_workspace_bytes(int num_pairs, int max_q, int top_k);
 
 /* ---- launch accounting and per-kernel timing (used by bench.py) ---------------------------- */
 /* Number of kernels this library has launched since it was loaded (all threads). */

@@ -239,3 +239,25 @@ def test_batched_pipeline_matches_per_crop_oracle():
             continue
         ref = ocorresp.establish_correspondences(pts[b, :counts[b]].cpu(), per_crop[b], bank_o, 5, 30)
         _check_corresp(ours, ref, 30)
+
+
+@pytest.mark.parametrize("nq,top_k", [(6000, 300), (40000, 300), (9000, 4096)])
+def test_cyclic_buddies_large_query_sets(nq, top_k):
+    """More than 4096 query points per crop (the reference's default grid_cell_size = 1 gives 176 400):
+    chunk-wise pre-selection + final sort must equal the oracle's canonical top-k."""
+    from foundpose_b200.utils import corresp_util, knn_util
+    from oracle import corresp as ocorresp
+
+    g = torch.Generator().manual_seed(nq)
+    obj = synthetic.fp16_representable(torch.randn(700, 64, generator=g))
+    q = synthetic.make_query_features(nq, 64, obj, seed=3, noise=0.5)
+    # points on a coarse lattice -> many exact ties in the cyclic distance
+    pts = torch.stack([torch.randint(0, 60, (nq,), generator=g), torch.randint(0, 60, (nq,), generator=g)], 1).float() * 7.0
+    qi = knn_util.KNN(1, "l2"); qi.fit(q.cuda())
+    oi = knn_util.KNN(1, "l2"); oi.fit(obj.cuda())
+    r = corresp_util.cyclic_buddies_matching(pts.cuda(), q.cuda(), qi, obj.cuda(), oi, top_k, False)
+    ro = ocorresp.cyclic_buddies_matching(pts, q, obj, top_k)
+    assert torch.equal(r[0].cpu(), ro[0])            # query ids, canonical tie order
+    assert torch.equal(r[1].cpu(), ro[1])            # object ids
+    assert torch.equal(r[2].cpu(), ro[2])            # distances
+    assert torch.allclose(r[3].cpu(), ro[3], equal_nan=True)
