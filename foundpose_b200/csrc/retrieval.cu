@@ -475,7 +475,9 @@ int cyclic_buddies(const float* points, const int* q_start, const int* q_count, 
   if (max_q > kCycMax) {
     // Large query sets (e.g. the reference's default grid_cell_size = 1 -> 176 400 points): reduce to
     // <= kCycMax candidates with chunk-wise pre-selection passes, then run the final sort.
-    FP_REQUIRE(top_k <= kCycMax, "cyclic_buddies: top_k=%d exceeds %d", top_k, kCycMax);
+    // every pass must shrink the candidate set: keep at most half a chunk
+    FP_REQUIRE(top_k <= kCycMax / 2, "cyclic_buddies: top_k=%d exceeds %d for more than %d query points",
+               top_k, kCycMax / 2, kCycMax);
     const size_t need = cyclic_buddies_workspace_bytes(num_pairs, max_q, top_k);
     FP_REQUIRE(workspace != nullptr && workspace_bytes >= need,
                "cyclic_buddies: %d query points per crop need a workspace of %zu bytes", max_q, need);
