@@ -70,7 +70,10 @@ class ObjectIndex:
         self.centroids16 = self.centroid_sqnorm = self.idfs = self.template_descs = self.desc_norm = None
         if getattr(repre, "feat_cluster_centroids", None) is not None:
             cent = repre.feat_cluster_centroids.to(dev, torch.float32)
-            self.centroids16 = _native.convert_rows_f16(_pad_cols(cent))
+            opts_ = getattr(repre, "template_desc_opts", None)
+            cosine_words = opts_ is not None and opts_.tfidf_knn_metric == "cosine"
+            # metric "cosine": visual words are L2-normalised at fit time (knn_util.py:61-64).
+            self.centroids16 = _native.convert_rows_f16(_pad_cols(cent), l2_normalize=cosine_words)
             self.centroid_sqnorm = _native.row_sqnorm_f16(self.centroids16)
         if getattr(repre, "feat_cluster_idfs", None) is not None:
             self.idfs = repre.feat_cluster_idfs.to(dev, torch.float32).contiguous()
@@ -80,6 +83,8 @@ class ObjectIndex:
         opts = getattr(repre, "template_desc_opts", None)
         self.tfidf_knn_k = opts.tfidf_knn_k if opts is not None else 3
         self.tfidf_knn_metric = opts.tfidf_knn_metric if opts is not None else "l2"
+        if self.tfidf_knn_metric not in ("l2", "cosine"):
+            raise ValueError(f"Metric {self.tfidf_knn_metric} is not supported.")
         self.tfidf_soft_assign = bool(opts.tfidf_soft_assign) if opts is not None else False
         self.tfidf_soft_sigma_squared = float(opts.tfidf_soft_sigma_squared) if opts is not None else 10.0
 
@@ -158,6 +163,7 @@ class RetrievalEngine:
         self.o2q_i = torch.zeros((npairs * self.max_p, 1), dtype=i64, device=dev)
         k = top_k_buddies
         self.cyc_workspace = _native.cyclic_buddies_workspace(npairs, stride, top_k_buddies, dev)
+        self.q_unit16 = self.q_unit_sqnorm = None
         self.out = MatchOutputs(
             template_ids=self.top_ids, template_scores=self.top_scores,
             count=torch.zeros((batch, self.topn), dtype=i32, device=dev),
@@ -173,11 +179,22 @@ class RetrievalEngine:
         """feat16 [B*stride, dpad] f16 query descriptors, points [B, stride, 2], q_count int32 [B]."""
         ix = self.index
         assert feat16.shape == (self.rows, ix.dim_padded), (feat16.shape, self.rows, ix.dim_padded)
-        metric = 0 if ix.tfidf_knn_metric == "l2" else 1
         _native.row_sqnorm_f16(feat16, self.q_sqnorm)
         # K1: nearest visual words of every query (template_util.py:13-29).
-        _native.knn_search_items(feat16, self.q_sqnorm, ix.centroids16, ix.centroid_sqnorm, self.items_words,
-                                 self.n_items_words, metric, self.knn_k, self.word_d, self.word_i)
+        if ix.tfidf_knn_metric == "l2":
+            _native.knn_search_items(feat16, self.q_sqnorm, ix.centroids16, ix.centroid_sqnorm, self.items_words,
+                                     self.n_items_words, 0, self.knn_k, self.word_d, self.word_i)
+        else:
+            # cosine: normalised copies of the queries, inner-product search, distance = 1 - similarity
+            # (knn_util.py:84-98).  Not the shipped configuration, so the copy is not fused.
+            if self.q_unit16 is None:
+                self.q_unit16 = torch.empty_like(feat16)
+                self.q_unit_sqnorm = torch.empty_like(self.q_sqnorm)
+            _native.convert_rows_f16(feat16.float(), l2_normalize=True, out=self.q_unit16)
+            _native.row_sqnorm_f16(self.q_unit16, self.q_unit_sqnorm)
+            _native.knn_search_items(self.q_unit16, self.q_unit_sqnorm, ix.centroids16, ix.centroid_sqnorm,
+                                     self.items_words, self.n_items_words, 1, self.knn_k, self.word_d, self.word_i)
+            torch.sub(1.0, self.word_d, out=self.word_d)
         _native.calc_tfidf(self.word_i, self.word_d, self.q_start, q_count, ix.idfs, ix.tfidf_soft_assign,
                            ix.tfidf_soft_sigma_squared, True, self.tfidf)
         _native.bow_scores(ix.template_descs, ix.desc_norm, self.tfidf, self.cos)

@@ -168,8 +168,9 @@ class DinoFeatureExtractor(nn.Module):
         self.model = Dinov2Weights(self.arch, state_dict)
 
         if self.stride != 14:
-            # patch_vit_resolution (reference :363-389) re-strides the patch conv; the B200 patch
-            # embedding is a non-overlapping 14x14 im2col GEMM.
+            # patch_vit_resolution (reference :363-389) re-strides the patch conv, but the method it
+            # installs (:324, bound at :386) takes one positional too few and raises TypeError on the
+            # first forward, so there is no reference behaviour to reproduce.
             raise NotImplementedError("foundpose_b200 supports the DINOv2 training stride (14) only.")
         self.patch_size: int = self.arch.patch_size
         self.max_batch = max_batch

@@ -261,3 +261,38 @@ def test_cyclic_buddies_large_query_sets(nq, top_k):
     assert torch.equal(r[1].cpu(), ro[1])            # object ids
     assert torch.equal(r[2].cpu(), ro[2])            # distances
     assert torch.allclose(r[3].cpu(), ro[3], equal_nan=True)
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_engine_cosine_visual_word_metric(soft):
+    """tfidf_knn_metric="cosine" through the batched engine == oracle tfidf_matching(knn_metric="cosine")."""
+    from foundpose_b200 import pipeline
+    from foundpose_b200.utils import repre_util
+    from oracle import knn as oknn, template as otemplate
+
+    T, P, d, W, B, nq = 30, 64, 128, 48, 3, 80
+    bank = synthetic.make_bank_tensors(T, P, d, num_words=W, seed=5)
+    feat = bank["feat_vectors"]
+    f2w = oknn.knn_l2(feat, bank["feat_cluster_centroids"], 1)[1].flatten()
+    descs, idfs = otemplate.calc_tfidf_descriptors(feat, f2w, bank["feat_to_template_ids"],
+                                                   bank["feat_cluster_centroids"], T, 3, False, 10.0)
+    opts = repre_util.TemplateDescOpts(tfidf_knn_metric="cosine", tfidf_soft_assign=soft, tfidf_soft_sigma_squared=0.05)
+    repre = repre_util.FeatureBasedObjectRepre(
+        vertices=bank["vertices"], feat_vectors=feat, feat_to_template_ids=bank["feat_to_template_ids"],
+        feat_cluster_centroids=bank["feat_cluster_centroids"], feat_cluster_idfs=idfs, template_descs=descs,
+        template_desc_opts=opts)
+    index = pipeline.ObjectIndex(repre, torch.device("cuda"))
+    engine = pipeline.RetrievalEngine(index, B, nq, 5, 20)
+    qs = [synthetic.make_query_features(nq, d, feat, seed=40 + b) for b in range(B)]
+    pts = torch.rand(B, nq, 2, device="cuda") * 100
+    cnt = torch.full((B,), nq, dtype=torch.int32, device="cuda")
+    out = engine.match(torch.cat(qs).half().cuda().contiguous(), pts, cnt)
+    torch.cuda.synchronize()
+    for b in range(B):
+        ids, scores, tfidf, cos = otemplate.tfidf_matching(qs[b].half().float(), bank["feat_cluster_centroids"], idfs,
+                                                           descs, 5, 3, "cosine", soft, 0.05)
+        assert torch.allclose(out.query_tfidf[b].cpu(), tfidf, rtol=5e-3, atol=1e-6)
+        assert torch.allclose(out.cos_sims[b].cpu(), cos, rtol=0, atol=2e-4)
+        gap = (cos[ids][:-1] - cos[ids][1:]).min()
+        if gap > 1e-3:
+            assert torch.equal(out.template_ids[b].cpu(), ids)
