@@ -227,6 +227,42 @@ def pca_project(x16, comp16, bias, out_f32, out_f16=None) -> None:
          stream_ptr(x16.device))
 
 
+CROP_PARAM_STRIDE = 40
+
+
+def crop_warp(images: Optional[torch.Tensor], masks_u8: Optional[torch.Tensor], params: torch.Tensor,
+              crop_w: int, crop_h: int, out_images: Optional[torch.Tensor] = None,
+              out_masks: Optional[torch.Tensor] = None, out_boxes: Optional[torch.Tensor] = None):
+    """images [n_img, H, W, C] uint8 or fp32, masks [B, H, W] uint8, params [B, 40] fp64 (see the header)."""
+    require_cuda(params, "params", torch.float64)
+    b = params.shape[0]
+    assert params.shape[1] == CROP_PARAM_STRIDE
+    dev = params.device
+    n_img = c = 0
+    is_f32 = 0
+    if images is not None:
+        assert images.dtype in (torch.uint8, torch.float32) and images.is_cuda and images.is_contiguous()
+        n_img, h, w, c = images.shape
+        is_f32 = int(images.dtype == torch.float32)
+        if out_images is None:
+            out_images = torch.empty((b, c, crop_h, crop_w), dtype=torch.float32, device=dev)
+    box_ws = None
+    if masks_u8 is not None:
+        require_cuda(masks_u8, "masks", torch.uint8)
+        assert masks_u8.shape[0] == b
+        h, w = masks_u8.shape[1:]
+        if out_masks is None:
+            out_masks = torch.empty((b, crop_h, crop_w), dtype=torch.uint8, device=dev)
+        if out_boxes is None:
+            out_boxes = torch.empty((b, 4), dtype=torch.float32, device=dev)
+        box_ws = torch.empty((4 * b,), dtype=torch.int32, device=dev)
+    if images is not None and masks_u8 is not None:
+        assert tuple(images.shape[1:3]) == tuple(masks_u8.shape[1:]), "image / mask size mismatch"
+    call("fp_crop_warp", ptr(images), _i(is_f32), _i(n_img), _i(h), _i(w), _i(c), ptr(masks_u8), ptr(params), _i(b),
+         _i(crop_w), _i(crop_h), ptr(out_images), ptr(out_masks), ptr(out_boxes), ptr(box_ws), stream_ptr(dev))
+    return out_images, out_masks, out_boxes
+
+
 def filter_points_by_mask(points, masks_u8, out_points, out_ids, out_counts) -> None:
     require_cuda(points, "points", torch.float32)
     require_cuda(masks_u8, "masks", torch.uint8)

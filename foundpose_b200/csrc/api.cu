@@ -220,6 +220,15 @@ int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_
                               static_cast<cudaStream_t>(stream));
 }
 
+int fp_crop_warp(const void* images, int src_is_f32, int num_images, int src_h, int src_w,
+                 int channels, const uint8_t* masks, const double* params, int B, int crop_w,
+                 int crop_h, float* out_images, uint8_t* out_masks, float* out_boxes,
+                 int32_t* box_workspace, void* stream) {
+  return fp::crop_warp(images, src_is_f32, num_images, src_h, src_w, channels, masks, params, B,
+                       crop_w, crop_h, out_images, out_masks, out_boxes, box_workspace,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int fp_filter_points_by_mask(const float* points, int num_points, const uint8_t* masks, int B,
                              int H, int W, float* out_points, int32_t* out_ids,
                              int32_t* out_counts, int out_stride, void* stream) {

@@ -84,6 +84,12 @@ int knn_search_items(const __half* q, long q_rows_total, const __half* x, long x
                      int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream);
 
 
+// ---- crop_warp.cu -----------------------------------------------------------------------
+int crop_warp(const void* images, int src_is_f32, int num_images, int src_h, int src_w, int channels,
+              const uint8_t* masks, const double* params, int B, int crop_w, int crop_h,
+              float* out_images, uint8_t* out_masks, float* out_boxes, int* box_workspace,
+              cudaStream_t stream);
+
 // ---- feature_ops.cu ---------------------------------------------------------------------
 int filter_points_by_mask(const float* points, int num_points, const uint8_t* masks, int B, int H,
                           int W, float* out_points, int* out_ids, int* out_counts, int out_stride,

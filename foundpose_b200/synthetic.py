@@ -20,7 +20,9 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
 
 import torch
 
@@ -209,3 +211,59 @@ def make_query_features(num_queries: int, feat_dim: int, bank_feats: Optional[to
     ids = torch.randint(0, bank_feats.shape[0], (num_queries,), generator=g)
     q = bank_feats[ids] + noise * torch.randn(num_queries, feat_dim, generator=g)
     return fp16_representable(q)
+
+
+def _rigid_transform(rng: np.random.RandomState, max_angle: float = 0.6) -> np.ndarray:
+    """Seeded 4x4 camera-to-world rigid transform (Rodrigues rotation + translation), float64."""
+    axis = rng.randn(3)
+    axis /= np.linalg.norm(axis)
+    angle = rng.uniform(-max_angle, max_angle)
+    k = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    T = np.eye(4)
+    T[:3, :3] = np.eye(3) + math.sin(angle) * k + (1 - math.cos(angle)) * (k @ k)
+    T[:3, 3] = rng.uniform(-0.5, 0.5, size=3)
+    return T
+
+
+def make_scene_image(height: int, width: int, seed: int = 0) -> np.ndarray:
+    """Seeded uint8 HWC image: smooth colour gradients plus per-pixel noise (so interpolation matters)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
+    chans = []
+    for c in range(3):
+        a, b, ph = rng.uniform(0.02, 0.15, size=3)
+        chans.append(127 + 80 * np.sin(a * xx + ph * 10) * np.cos(b * yy) + rng.randint(-30, 31, size=(height, width)))
+    return np.clip(np.stack(chans, axis=-1), 0, 255).astype(np.uint8)
+
+
+def make_instance_mask(height: int, width: int, center: Tuple[float, float], radii: Tuple[float, float],
+                       seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Seeded elliptical uint8 {0,1} modal mask with a few holes, and its amodal box (left, top, right, bottom)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
+    inside = ((xx - center[0]) / radii[0]) ** 2 + ((yy - center[1]) / radii[1]) ** 2 <= 1.0
+    holes = rng.rand(height, width) < 0.05
+    mask = (inside & ~holes).astype(np.uint8)
+    box = np.array([center[0] - radii[0], center[1] - radii[1], center[0] + radii[0], center[1] + radii[1]])
+    return mask, box
+
+
+def make_crop_cases() -> List[Dict[str, object]]:
+    """Small crop-stage cases (shared by tests/golden/make_golden_crop.py and the parity tests)."""
+    cases: List[Dict[str, object]] = []
+    specs = [
+        # (center, radii, crop_size (W, H), rel_pad, identity pose?)   what it exercises
+        ((60.0, 45.0), (20.0, 15.0), (56, 56), 0.2, True),     # magnification -> INTER_LINEAR
+        ((64.0, 48.0), (50.0, 40.0), (28, 28), 0.2, False),    # minification -> INTER_AREA (same remap path)
+        ((8.0, 20.0), (18.0, 16.0), (42, 42), 0.3, False),     # box leaves the image -> constant border
+        ((100.0, 70.0), (22.0, 24.0), (56, 42), 0.1, False),   # non-square viewport, fx != fy
+    ]
+    for i, (center, radii, crop_size, pad, identity) in enumerate(specs):
+        rng = np.random.RandomState(100 + i)
+        mask, box = make_instance_mask(96, 128, center, radii, seed=200 + i)
+        cases.append({
+            "image": make_scene_image(96, 128, seed=300 + i), "mask": mask, "box": box,
+            "f": (110.0, 110.0) if i < 3 else (120.0, 104.0), "c": (63.5, 47.5),
+            "T_world_from_eye": np.eye(4) if identity else _rigid_transform(rng),
+            "crop_size": crop_size, "crop_rel_pad": pad})
+    return cases

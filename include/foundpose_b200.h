@@ -166,6 +166,22 @@ int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_
                         int dim, const fp_knn_item* items, int num_items, int metric, int k,
                         float* out_d, int64_t* out_i, void* stream);
 
+/* ---- crop stage in front of the extractor ------------------------- */
+/* warp_image x2 + array_to_tensor + calc_2d_box for B instances (scripts/infer.py:427-456,
+ * utils/misc.py:458-519, cv2.remap semantics).  images: [num_images, src_h, src_w, channels]
+ * interleaved, uint8 (scaled by 1/255 like infer.py:396) or fp32 when src_is_f32; masks: uint8
+ * [B, src_h, src_w] modal masks or NULL.  params: double [B, 40] per instance:
+ *   [0:2] f and [2:4] c of the virtual crop camera, [4:13] R and [13:16] t of its T_world_from_eye
+ *   (row-major), [16:25] R and [25:28] t of the source camera's T_world_from_eye, [28:30] f and
+ *   [30:32] c of the source camera, [32] index of the source image, [33:40] reserved.
+ * Writes out_images fp32 [B, channels, crop_h, crop_w] (INTER_LINEAR == INTER_AREA inside remap,
+ * constant border 0), out_masks uint8 [B, crop_h, crop_w] (INTER_NEAREST) and out_boxes fp32 [B,4]
+ * = (x1,y1,x2,y2) of the warped mask, zeros when it is empty.  box_workspace: int32 [4*B]. */
+int fp_crop_warp(const void* images, int src_is_f32, int num_images, int src_h, int src_w,
+                 int channels, const uint8_t* masks, const double* params, int B, int crop_w,
+                 int crop_h, float* out_images, uint8_t* out_masks, float* out_boxes,
+                 int32_t* box_workspace, void* stream);
+
 /* ---- query points and feature sampling ---------------------------------------------------- */
 /* filter_points_by_mask (utils/feature_util.py:75-97) for B crops sharing one point grid:
  * keeps points whose rounded pixel lies strictly inside the canvas and inside masks[b] (uint8,
