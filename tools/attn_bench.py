@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Isolated attention timing with experiment switches (results are WRONG when a switch is set)."""
+"""Isolated attention timing over the launcher's kernel variants (share of exponentials on the FMA
+pipe), each checked against an fp32 torch softmax(QK^T)V on the same fp16 inputs."""
 import ctypes
 import os
 import sys
@@ -11,14 +12,25 @@ import torch  # noqa: E402
 from foundpose_b200 import _native  # noqa: E402
 
 B, N, H = 64, 901, 16
+VARIANTS = [("1thr/row 24|24", 1), ("1thr/row 0|0", 2), ("1thr/row 16|16", 3), ("1thr/row 32|32", 4), ("2thr/row 0|0", 5),
+            ("2thr/row 16|16", 6), ("2thr/row 8|24", 7), ("default", 0)]
 g = torch.Generator().manual_seed(0)
-qkv = (torch.randn(B * N, 3 * H * 64, generator=g)).half().cuda()
+qkv = (torch.randn(B * N, 3 * H * 64, generator=g) * 1.5).half().cuda()
 lib = _native.load()
+
+
+def reference(b):
+    x = qkv[b * N:(b + 1) * N].float().view(N, 3, H, 64).permute(1, 2, 0, 3)   # [3, H, N, 64]
+    att = torch.softmax(x[0] @ x[1].transpose(1, 2) * 0.125, dim=-1)
+    return (att @ x[2]).permute(1, 0, 2).reshape(N, H * 64)
+
+
+ref0 = reference(0)
 for rep in range(2):
-    for name, fl in [("baseline", 0)]:
+    for name, fl in VARIANTS:
         lib.fp_gemm_force_1sm(ctypes.c_int(fl << 16))
         for _ in range(3):
-            _native.attention_f16(qkv, B, N, H)
+            out = _native.attention_f16(qkv, B, N, H)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
@@ -26,5 +38,6 @@ for rep in range(2):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 10 * 1e3
-        print(f"rep{rep} {name:18s} {us:7.1f} us  {4.0 * B * H * N * N * 64 / us / 1e6:6.1f} TFLOP/s")
+        err = ((out[:N].float() - ref0).norm() / ref0.norm()).item()
+        print(f"rep{rep} {name:16s} {us:7.1f} us  {4.0 * B * H * N * N * 64 / us / 1e6:6.1f} TFLOP/s  rel_err {err:.2e}", flush=True)
 lib.fp_gemm_force_1sm(ctypes.c_int(0))

@@ -34,9 +34,9 @@ rows.sort()
 t0 = rows[0][0]
 limit = int(sys.argv[1]) if len(sys.argv) > 1 else 140
 for t, r, tag in rows[:limit]:
-    print(f"{t - t0:8d} ns  {roles[r]:10s} tag={tag}")
+    print(f"{t - t0:8d} cyc {roles[r]:10s} tag={tag}")
 # per-item duration seen by softmax A (tag 90 = drain)
 drains = [t for t, r, tag in rows if r == 3 and tag == 90]
 if len(drains) > 2:
     d = [b - a for a, b in zip(drains, drains[1:])]
-    print("item period (ns) seen by softmax A:", d[:12], "mean", sum(d) / len(d))
+    print("item period (SM cycles) seen by softmax A:", d[:12], "mean", sum(d) / len(d))
