@@ -313,6 +313,33 @@ def build_pair_items(top_ids, topn, tpl_off, q_start, q_count, max_q, max_p, ite
          _i(max_q), _i(max_p), ptr(items_q2o), ptr(items_o2q), stream_ptr(top_ids.device))
 
 
+def pnp_ransac(coord_2d, coord_3d, counts, intrinsics, iters: int, thresh: float, confidence: float, seed: int,
+               problem_offset: int = 0):
+    """fp_pnp_ransac over P problems; returns a dict of freshly allocated device tensors."""
+    require_cuda(coord_2d, "coord_2d", torch.float32)
+    require_cuda(coord_3d, "coord_3d", torch.float32)
+    require_cuda(counts, "counts", torch.int32)
+    require_cuda(intrinsics, "intrinsics", torch.float64)
+    P, M = coord_2d.shape[0], coord_2d.shape[1]
+    if coord_3d.shape != (P, M, 3) or coord_2d.shape != (P, M, 2) or counts.shape != (P,) or intrinsics.shape != (P, 4):
+        raise ValueError("pnp_ransac: expected coord_2d [P,M,2], coord_3d [P,M,3], counts [P], intrinsics [P,4]")
+    dev = coord_2d.device
+    out = {
+        "success": torch.zeros(P, dtype=torch.int32, device=dev),
+        "R": torch.zeros(P, 3, 3, dtype=torch.float64, device=dev),
+        "t": torch.zeros(P, 3, dtype=torch.float64, device=dev),
+        "inlier_mask": torch.zeros(P, M, dtype=torch.uint8, device=dev),
+        "num_inliers": torch.zeros(P, dtype=torch.int32, device=dev),
+        "iters_run": torch.zeros(P, dtype=torch.int32, device=dev),
+        "best_hyp": torch.zeros(P, dtype=torch.int32, device=dev),
+    }
+    call("fp_pnp_ransac", ptr(coord_2d), ptr(coord_3d), ptr(counts), ptr(intrinsics), _i(P), _i(M), _i(iters),
+         ctypes.c_double(thresh), ctypes.c_double(confidence), ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF),
+         _i(problem_offset), ptr(out["success"]), ptr(out["R"]), ptr(out["t"]), ptr(out["inlier_mask"]),
+         ptr(out["num_inliers"]), ptr(out["iters_run"]), ptr(out["best_hyp"]), stream_ptr(dev))
+    return out
+
+
 def cyclic_buddies_workspace(num_pairs: int, max_q: int, top_k: int, device) -> Optional[torch.Tensor]:
     lib = load()
     lib.fp_cyclic_buddies_workspace_bytes.restype = ctypes.c_uint64

@@ -261,6 +261,16 @@ int fp_bow_scores(const float* descs, const float* desc_norm, const float* q, in
   return fp::bow_scores(descs, desc_norm, q, T, B, W, out, static_cast<cudaStream_t>(stream));
 }
 
+int fp_pnp_ransac(const float* coord_2d, const float* coord_3d, const int32_t* counts,
+                  const double* intrinsics, int P, int M, int iters, double thresh, double confidence,
+                  uint64_t seed, int problem_offset, int32_t* success, double* out_R, double* out_t,
+                  uint8_t* inlier_mask, int32_t* num_inliers, int32_t* iters_run, int32_t* best_hyp,
+                  void* stream) {
+  return fp::pnp_ransac(coord_2d, coord_3d, counts, intrinsics, P, M, iters, thresh, confidence, seed,
+                        problem_offset, success, out_R, out_t, inlier_mask, num_inliers, iters_run, best_hyp,
+                        static_cast<cudaStream_t>(stream));
+}
+
 int fp_topk_rows(const float* x, int rows, int cols, int k, float* out_v, int64_t* out_i,
                  void* stream) {
   return fp::topk_rows(x, rows, cols, k, out_v, out_i, static_cast<cudaStream_t>(stream));

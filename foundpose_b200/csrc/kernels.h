@@ -118,4 +118,10 @@ int cyclic_buddies(const float* points, const int* q_start, const int* q_count, 
                    size_t workspace_bytes, cudaStream_t stream);
 size_t cyclic_buddies_workspace_bytes(int num_pairs, int max_q, int top_k);
 
+// ---- pnp_ransac.cu ----------------------------------------------------------------------
+int pnp_ransac(const float* coord_2d, const float* coord_3d, const int* counts, const double* intrinsics, int P,
+               int M, int iters, double thresh, double confidence, unsigned long long seed, int problem_offset,
+               int* success, double* out_R, double* out_t, unsigned char* inlier_mask, int* num_inliers,
+               int* iters_run, int* best_hyp, cudaStream_t stream);
+
 }  // namespace fp

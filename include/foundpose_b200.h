@@ -240,6 +240,25 @@ int fp_cyclic_buddies(const float* points, const int32_t* q_start, const int32_t
                       uint64_t workspace_bytes, void* stream);
 uint64_t fp_cyclic_buddies_workspace_bytes(int num_pairs, int max_q, int top_k);
 
+/* ---- coarse pose from the correspondences --------------------------- */
+/* Replaces the per-template host loop scripts/infer.py:551-577 -> utils/pnp_util.py:42-72
+ * (cv2.solvePnPRansac(flags=SOLVEPNP_ITERATIVE) + cv2.solvePnPRefineLM) for P problems at once,
+ * one problem = one (crop, template) pair = the output of fp_cyclic_buddies for that pair.
+ *   coord_2d fp32 [P,M,2], coord_3d fp32 [P,M,3], counts int32 [P] (valid correspondences, <= M),
+ *   intrinsics fp64 [P,4] = fx, fy, cx, cy of the crop camera (utils/misc.py:325-341).
+ * RANSAC: `iters` hypotheses per problem (hypothesis h of problem problem_offset + p samples 4
+ * distinct correspondences from a splitmix64 stream keyed by (seed, problem, h), P3P on three,
+ * fourth disambiguates), inlier <=> squared reprojection error <= thresh^2, sequential semantics
+ * incl. OpenCV's RANSACUpdateNumIters(confidence) evaluated by one scan over the per-hypothesis
+ * inlier counts; then Levenberg-Marquardt on the inliers (float64).  See oracle/pnp.py.
+ * Outputs: success int32 [P] (>= 6 inliers), R fp64 [P,9] row-major and t fp64 [P,3] (model ->
+ * camera), inlier_mask uint8 [P,M], num_inliers / iters_run / best_hyp int32 [P]. */
+int fp_pnp_ransac(const float* coord_2d, const float* coord_3d, const int32_t* counts,
+                  const double* intrinsics, int P, int M, int iters, double thresh, double confidence,
+                  uint64_t seed, int problem_offset, int32_t* success, double* out_R, double* out_t,
+                  uint8_t* inlier_mask, int32_t* num_inliers, int32_t* iters_run, int32_t* best_hyp,
+                  void* stream);
+
 /* ---- launch accounting and per-kernel timing (used by bench.py) ---------------------------- */
 /* Number of kernels this library has launched since it was loaded (all threads). */
 unsigned long long fp_launch_count(void);
