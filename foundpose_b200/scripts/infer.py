@@ -3,10 +3,10 @@
 
 `InferOpts` has the same fields and defaults as the reference (scripts/infer.py:55-100) and is read
 from `--opts-path <json>` under the key "infer_opts" (utils/config_util.py:254-278) or from flags.
-The reference's dataset plumbing (BOP images, CNOS detections, cameras, PnP, evaluation, rendering)
-is outside the scope of this build; what this script runs is the per-instance block
-scripts/infer.py:467-545 - extractor -> mask filter -> sampling -> PCA -> establish_correspondences -
-on crops you provide (`--crops <file.pt>` with tensors "images" Bx3xHxW in [0,1] and "masks" BxHxW)
+The reference's dataset plumbing (BOP images, CNOS detections, evaluation, rendering) is outside the
+scope of this build; what this script runs is the per-instance block
+scripts/infer.py:467-604 - extractor -> mask filter -> sampling -> PCA -> establish_correspondences ->
+coarse pose per retrieved template (PnP-RANSAC) -> best coarse pose - on crops you provide (`--crops <file.pt>` with tensors "images" Bx3xHxW in [0,1] and "masks" BxHxW)
 against a `repre.pth` object representation (`--repre-dir`), or on seeded synthetic crops and a
 synthetic representation when neither is given (`--synthetic`).
 
@@ -32,7 +32,7 @@ if _ROOT not in sys.path:
 
 from foundpose_b200 import distributed, pipeline, synthetic  # noqa: E402
 from foundpose_b200.utils import (corresp_util, feature_util, knn_util, logging, misc,  # noqa: E402
-                                  projector_util, repre_util, template_util)
+                                  pnp_util, projector_util, repre_util, structs, template_util)
 
 
 class InferOpts(NamedTuple):
@@ -65,7 +65,7 @@ class InferOpts(NamedTuple):
     match_feat_matching_type: str = "cyclic_buddies"
     match_top_k_buddies: int = 300
 
-    # PnP options (kept for config compatibility; PnP is out of scope here).
+    # PnP options.
     pnp_type: str = "opencv"
     pnp_ransac_iter: int = 1000
     pnp_required_ransac_conf: float = 0.99
@@ -152,6 +152,34 @@ def infer_instance(opts: InferOpts, extractor, repre, grid_points, image_chw: to
     return corresp, times
 
 
+def estimate_coarse_poses(opts: InferOpts, corresp: List[Dict], camera_c2w: structs.PinholePlaneCameraModel,
+                          seed: int = 0) -> Tuple[List[Dict[str, Any]], int]:
+    """Coarse pose per retrieved template and the best one (scripts/infer.py:551-604), same control flow."""
+    coarse_poses: List[Dict[str, Any]] = []
+    for corresp_id, corresp_curr in enumerate(corresp):
+        num_corresp = len(corresp_curr["coord_2d"])
+        if num_corresp < 6:
+            continue
+        ok, R_m2c, t_m2c, inliers, quality = pnp_util.estimate_pose(
+            corresp=corresp_curr, camera_c2w=camera_c2w, pnp_type=opts.pnp_type,
+            pnp_ransac_iter=opts.pnp_ransac_iter, pnp_inlier_thresh=opts.pnp_inlier_thresh,
+            pnp_required_ransac_conf=opts.pnp_required_ransac_conf, pnp_refine_lm=opts.pnp_refine_lm, seed=seed)
+        if ok:
+            coarse_poses.append({"type": "coarse", "R_m2c": R_m2c, "t_m2c": t_m2c, "corresp_id": corresp_id,
+                                 "quality": quality, "inliers": inliers})
+    best_quality, best_id = None, 0
+    for pose_id, pose in enumerate(coarse_poses):
+        if best_quality is None or pose["quality"] > best_quality:
+            best_id, best_quality = pose_id, pose["quality"]
+    return coarse_poses, best_id
+
+
+def default_crop_camera(crop_size: Tuple[int, int]) -> structs.PinholePlaneCameraModel:
+    """Camera used when crops come without one (synthetic mode): f = 600 px, principal point at the centre."""
+    return structs.PinholePlaneCameraModel(crop_size[0], crop_size[1], (600.0, 600.0),
+                                           (crop_size[0] / 2.0, crop_size[1] / 2.0))
+
+
 def make_synthetic_repre(extractor_dim: int, feat_dim: int, templates: int, patches: int, words: int,
                          device: torch.device, seed: int = 0) -> repre_util.FeatureBasedObjectRepre:
     bank = synthetic.make_bank_tensors(templates, patches, feat_dim, num_words=words, seed=seed)
@@ -209,6 +237,8 @@ def infer(opts: InferOpts, repre_dir: Optional[str] = None, crops_path: Optional
     logging.log_heading(logger, f"Object representation: {index.num_templates} templates, "
                                 f"{index.bank16.shape[0]} features, vertices: {len(repre.vertices)}")
     results: List[Dict[str, Any]] = []
+    camera_c2w = default_crop_camera(opts.crop_size)
+    intrinsics = torch.from_numpy(pnp_util.get_intrinsics_vector(camera_c2w)).to(device).reshape(1, 4)
     if batch > 0:
         pipe = pipeline.CropBatchPipeline(extractor, index, repre.feat_raw_projectors, batch,
                                           crop_size=opts.crop_size, grid_cell_size=opts.grid_cell_size,
@@ -223,17 +253,33 @@ def infer(opts: InferOpts, repre_dir: Optional[str] = None, crops_path: Optional
                 img = torch.cat([img, img[:1].expand(batch - (e - s), -1, -1, -1)])
                 msk = torch.cat([msk, torch.zeros((batch - (e - s),) + msk.shape[1:], dtype=torch.uint8, device=device)])
             out = pipe.run(img.contiguous(), msk.contiguous())
+            # Coarse poses of all (crop, template) pairs of the batch in one launch.
+            topn, kk = out.count.shape[1], out.coord_2d.shape[2]
+            poses = pnp_util.estimate_poses_batched(
+                out.coord_2d.reshape(batch * topn, kk, 2), out.coord_3d.reshape(batch * topn, kk, 3),
+                out.count.reshape(-1), intrinsics.expand(batch * topn, 4).contiguous(), opts.pnp_ransac_iter,
+                opts.pnp_inlier_thresh, opts.pnp_required_ransac_conf, problem_offset=(start + s) * topn)
+            best = pnp_util.select_best_poses(poses["success"], poses["num_inliers"], topn).cpu()
+            poses = {k: v.cpu() for k, v in poses.items()}
             for b in range(e - s):
                 corresp = pipeline.outputs_to_corresp_list(out, b)
+                j = int(best[b])
                 results.append({"crop_id": start + s + b, "corresp": [
-                    {k: v.cpu().clone() for k, v in c.items()} for c in corresp]})
+                    {k: v.cpu().clone() for k, v in c.items()} for c in corresp],
+                    "best_coarse_pose": None if j < 0 else {
+                        "corresp_id": j, "R_m2c": poses["R"][b * topn + j].numpy(),
+                        "t_m2c": poses["t"][b * topn + j].numpy().reshape(3, 1),
+                        "quality": float(poses["num_inliers"][b * topn + j])}})
     else:
         for i in range(images.shape[0]):
             corresp, times = infer_instance(opts, extractor, repre, grid_points, images[i], masks[i],
                                             visual_words_knn_index, template_knn_indices)
             logger.info(f"Number of corresp: {[len(c['coord_2d']) for c in corresp]}")
+            coarse_poses, best_id = estimate_coarse_poses(opts, corresp, camera_c2w)
             results.append({"crop_id": start + i, "time": times,
-                            "corresp": [{k: v.cpu() for k, v in c.items()} for c in corresp]})
+                            "corresp": [{k: v.cpu() for k, v in c.items()} for c in corresp],
+                            "coarse_poses": coarse_poses,
+                            "best_coarse_pose": coarse_poses[best_id] if coarse_poses else None})
     if output_path is not None:
         suffix = f".rank{rank}" if world > 1 else ""
         torch.save(results, output_path + suffix)

@@ -20,6 +20,11 @@ def test_per_crop_and_batched_modes_agree(monkeypatch):
     assert len(a) == len(b) == 5
     for ra, rb in zip(a, b):
         assert ra["crop_id"] == rb["crop_id"]
+        # coarse-pose block runs in both modes (synthetic correspondences carry no geometry: a pose may be None)
+        assert "best_coarse_pose" in ra and "best_coarse_pose" in rb
+        for r in (ra, rb):
+            if r["best_coarse_pose"] is not None:
+                assert r["best_coarse_pose"]["R_m2c"].shape == (3, 3) and r["best_coarse_pose"]["quality"] >= 6
         if len(ra["corresp"]) == 0:          # empty mask -> the per-crop path returns no correspondences
             assert all(len(c["coord_2d"]) == 0 for c in rb["corresp"])
             continue
