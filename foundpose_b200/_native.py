@@ -313,6 +313,17 @@ def build_pair_items(top_ids, topn, tpl_off, q_start, q_count, max_q, max_p, ite
          _i(max_q), _i(max_p), ptr(items_q2o), ptr(items_o2q), stream_ptr(top_ids.device))
 
 
+def kmeans_update(samples: torch.Tensor, assign: torch.Tensor, k: int, sums: torch.Tensor, counts: torch.Tensor,
+                  centroids: torch.Tensor) -> None:
+    require_cuda(samples, "samples", torch.float32)
+    require_cuda(assign, "assign", torch.int64)
+    require_cuda(centroids, "centroids", torch.float32)
+    n, d = samples.shape
+    assert sums.dtype == torch.int64 and sums.numel() == k * d and counts.dtype == torch.int32 and counts.numel() == k
+    call("fp_kmeans_update", ptr(samples), ptr(assign), _l(n), _i(d), _i(k), ptr(sums), ptr(counts), ptr(centroids),
+         stream_ptr(samples.device))
+
+
 def pnp_ransac(coord_2d, coord_3d, counts, intrinsics, iters: int, thresh: float, confidence: float, seed: int,
                problem_offset: int = 0):
     """fp_pnp_ransac over P problems; returns a dict of freshly allocated device tensors."""

@@ -261,6 +261,12 @@ int fp_bow_scores(const float* descs, const float* desc_norm, const float* q, in
   return fp::bow_scores(descs, desc_norm, q, T, B, W, out, static_cast<cudaStream_t>(stream));
 }
 
+int fp_kmeans_update(const float* samples, const int64_t* assign, int64_t n, int d, int k, uint64_t* sums,
+                     int32_t* counts, float* centroids, void* stream) {
+  return fp::kmeans_update(samples, assign, n, d, k, reinterpret_cast<unsigned long long*>(sums), counts, centroids,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int fp_pnp_ransac(const float* coord_2d, const float* coord_3d, const int32_t* counts,
                   const double* intrinsics, int P, int M, int iters, double thresh, double confidence,
                   uint64_t seed, int problem_offset, int32_t* success, double* out_R, double* out_t,

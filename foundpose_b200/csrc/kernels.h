@@ -118,6 +118,10 @@ int cyclic_buddies(const float* points, const int* q_start, const int* q_count, 
                    size_t workspace_bytes, cudaStream_t stream);
 size_t cyclic_buddies_workspace_bytes(int num_pairs, int max_q, int top_k);
 
+// ---- kmeans.cu --------------------------------------------------------------------------
+int kmeans_update(const float* x, const int64_t* assign, long long n, int d, int k, unsigned long long* sums,
+                  int* counts, float* centroids, cudaStream_t stream);
+
 // ---- pnp_ransac.cu ----------------------------------------------------------------------
 int pnp_ransac(const float* coord_2d, const float* coord_3d, const int* counts, const double* intrinsics, int P,
                int M, int iters, double thresh, double confidence, unsigned long long seed, int problem_offset,

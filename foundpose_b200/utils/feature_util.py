@@ -79,3 +79,54 @@ def sample_feature_map_at_points(feature_map_chw: torch.Tensor, points: torch.Te
             raise ValueError("feature dimension must be a multiple of 4")
         _native.sample_features(tokens, h, w, pts, None, float(image_size[0]), float(image_size[1]), out, None)
     return out
+
+
+def lift_2d_points_to_3d(points: torch.Tensor, depth_image: torch.Tensor, camera_model) -> torch.Tensor:
+    """3D camera-space points of 2D image points with a depth image (reference utils/feature_util.py:132-155).
+
+    Index arithmetic and a gather on O(1000) points, evaluated with the same torch calls as the reference.
+    """
+    device = points.device
+    focal = 0.5 * (camera_model.f[0] + camera_model.f[1])    # the reference uses the average of fx and fy
+    points_3d_in_cam = torch.hstack([
+        points - torch.as_tensor(camera_model.c).to(torch.float32).to(device),
+        focal * torch.ones(points.shape[0], 1).to(torch.float32).to(device),
+    ])
+    depths = depth_image[torch.floor(points[:, 1]).to(torch.int64), torch.floor(points[:, 0]).to(torch.int64)].reshape(-1, 1)
+    points_3d_in_cam = points_3d_in_cam * (depths / points_3d_in_cam[:, 2].reshape(-1, 1))
+    return points_3d_in_cam
+
+
+def erode_mask_5x5(object_mask: torch.Tensor) -> torch.Tensor:
+    """`kornia.morphology.erosion(mask, ones(5, 5))` (reference :181-188): minimum over the 5x5 window,
+    pixels outside the image do not erode (kornia's default geodesic border)."""
+    m = object_mask.reshape(1, 1, *object_mask.shape).to(torch.float32)
+    eroded = -torch.nn.functional.max_pool2d(-m, kernel_size=5, stride=1, padding=2)
+    return eroded.reshape(object_mask.shape).to(object_mask.dtype)
+
+
+def get_visual_features_registered_in_3d(image_chw: torch.Tensor, depth_image_hw: torch.Tensor,
+                                         object_mask: torch.Tensor, camera, T_model_from_camera: torch.Tensor,
+                                         extractor: torch.nn.Module, grid_cell_size: float, debug: bool = False,
+                                         feature_map_chw: torch.Tensor = None
+                                         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Features of one template registered in 3D (reference utils/feature_util.py:158-241), same outputs:
+    (feat_vectors [n, C], vertex_ids [n] int32, vertices_in_model [n, 3]).
+
+    `feature_map_chw` lets the offline bank build pass the map of this template out of a BATCHED
+    extractor call (scripts/gen_repre.py runs the extractor once per template).
+    """
+    device = image_chw.device
+    grid_points = generate_grid_points(grid_size=(image_chw.shape[2], image_chw.shape[1]),
+                                       cell_size=grid_cell_size).to(device)
+    object_mask_eroded = erode_mask_5x5(object_mask)
+    query_points = filter_points_by_mask(grid_points, object_mask_eroded)
+    vertices_in_cam = lift_2d_points_to_3d(points=query_points, depth_image=depth_image_hw, camera_model=camera)
+    T = T_model_from_camera.to(device, torch.float32)
+    vertices_in_model = vertices_in_cam @ T[:3, :3].T + T[:3, 3]          # geometry.transform_3d_points_torch
+    vertex_ids = torch.arange(vertices_in_model.shape[0], dtype=torch.int32)
+    if feature_map_chw is None:
+        feature_map_chw = extractor(image_chw.unsqueeze(0))["feature_maps"][0]
+    feat_vectors = sample_feature_map_at_points(feature_map_chw=feature_map_chw, points=query_points,
+                                                image_size=(image_chw.shape[-1], image_chw.shape[-2])).detach()
+    return feat_vectors, vertex_ids, vertices_in_model

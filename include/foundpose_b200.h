@@ -240,6 +240,15 @@ int fp_cyclic_buddies(const float* points, const int32_t* q_start, const int32_t
                       uint64_t workspace_bytes, void* stream);
 uint64_t fp_cyclic_buddies_workspace_bytes(int num_pairs, int max_q, int top_k);
 
+/* ---- offline bank build: k-means centroid update -------------------- */
+/* One update step of faiss.Kmeans.train as used by utils/cluster_util.py:37-52 (faiss Clustering.cpp
+ * compute_centroids): centroids[c] = mean of the samples with assign == c, zero for empty clusters.
+ * samples fp32 [n,d], assign int64 [n] (rows outside [0,k) are ignored), sums uint64 [k,d] and
+ * counts int32 [k] are outputs / scratch (64-bit fixed-point sums, value * 2^24: order-independent,
+ * hence bit-reproducible), centroids fp32 [k,d].  The assignment step is fp_knn_search_items. */
+int fp_kmeans_update(const float* samples, const int64_t* assign, int64_t n, int d, int k, uint64_t* sums,
+                     int32_t* counts, float* centroids, void* stream);
+
 /* ---- coarse pose from the correspondences --------------------------- */
 /* Replaces the per-template host loop scripts/infer.py:551-577 -> utils/pnp_util.py:42-72
  * (cv2.solvePnPRansac(flags=SOLVEPNP_ITERATIVE) + cv2.solvePnPRefineLM) for P problems at once,
