@@ -429,6 +429,11 @@ def run_cuda_arm(args) -> None:
     h2d = int(host_images[0].numel() * 4 + host_masks[0].numel())
     d2h = int(sum(t.numel() * t.element_size() for t in d2h_fields))
 
+    # ---- explanatory extras (outside the timed regions, rank 0 at N=1) ------------------------------
+    extras = {}
+    if rank == 0 and world == 1:
+        extras = measure_extras(lib, pipe, dev, hbm_peak, B)
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -466,11 +471,79 @@ def run_cuda_arm(args) -> None:
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
 
         dist.destroy_process_group()
+
+
+def measure_extras(lib, pipe, dev, hbm_peak: float, B: int) -> dict:
+    """Two measurements that explain the headline but are not part of it:
+
+    * `knn_hbm`: the k-NN kernel in its bandwidth-bound pass structure (BASELINE metric "kNN HBM GB/s vs peak"):
+      one 128-query tile sweeps the bank of BASELINE configs[2] (10k templates x 1024 patches x 384-d fp16 =
+      7.9 GB, larger than L2) once; algorithmic bytes = F*d*2 per search over the knn_kernel's CUDA-event time.
+    * `coarse_pose`: fp_pnp_ransac on the correspondences of the last step (B x top-N problems, 400 iterations).
+    """
+    import ctypes
+
+    from foundpose_b200 import _native
+    from foundpose_b200.utils import knn_util, pnp_util
+
+    out = {}
+    try:
+        rows, dim, nq, iters = 10000 * 1024, 384, 128, 5
+        bank = torch.empty(rows, dim, device=dev, dtype=torch.float16)
+        for s0 in range(0, rows, 1 << 20):
+            bank[s0:s0 + (1 << 20)] = torch.randn(min(1 << 20, rows - s0), dim, device=dev, dtype=torch.float16)
+        index = knn_util.KNN.from_packed(bank, _native.row_sqnorm_f16(bank), k=5, metric="l2")
+        q = torch.randn(nq, dim, device=dev)
+        for _ in range(2):
+            index.search(q)
+        torch.cuda.synchronize()
+        for c in range(len(CATEGORY_NAMES)):
+            lib.fp_profile_read(ctypes.c_int(c), None, None, None, ctypes.c_int(1))
+        lib.fp_profile_enable(1)
+        for _ in range(iters):
+            index.search(q)
+        lib.fp_profile_enable(0)
+        ms, w, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        lib.fp_profile_read(ctypes.c_int(4), ctypes.byref(ms), ctypes.byref(w), ctypes.byref(n), ctypes.c_int(1))
+        for c in range(len(CATEGORY_NAMES)):
+            lib.fp_profile_read(ctypes.c_int(c), None, None, None, ctypes.c_int(1))
+        t = ms.value / iters * 1e-3
+        gbs = rows * dim * 2 / t / 1e9
+        out["knn_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                          "knn_kernel_ms": t * 1e3, "bank_bytes": rows * dim * 2,
+                          "workload": "128 queries x (10k templates x 1024 patches x 384-d fp16) bank of configs[2], "
+                                      "k=5, bank split over all SMs; more cases in profiles/r01_knn_bench.md"}
+        del index, bank, q
+        torch.cuda.empty_cache()
+    except Exception as e:   # never let an extra break the headline line
+        out["knn_hbm"] = {"error": repr(e)}
+    try:
+        o = pipe.engine.out
+        topn, kk = o.count.shape[1], o.coord_2d.shape[2]
+        intr = torch.tensor([[600.0, 600.0, 210.0, 210.0]], dtype=torch.float64, device=dev).expand(B * topn, 4).contiguous()
+        args_ = (o.coord_2d.reshape(B * topn, kk, 2), o.coord_3d.reshape(B * topn, kk, 3), o.count.reshape(-1), intr,
+                 400, 10.0, 0.99)
+        for _ in range(2):
+            pnp_util.estimate_poses_batched(*args_)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            pnp_util.estimate_poses_batched(*args_)
+        e1.record()
+        torch.cuda.synchronize()
+        out["coarse_pose"] = {"ms_per_step": e0.elapsed_time(e1) / 5, "problems_per_step": B * topn,
+                              "correspondences": kk, "ransac_iterations": 400,
+                              "note": "fp_pnp_ransac on the step's correspondences; not inside the timed regions "
+                                      "(the north-star path ends at the correspondences)"}
+    except Exception as e:
+        out["coarse_pose"] = {"error": repr(e)}
+    return out
 
 
 def vit_flops_per_crop(arch, layer: int, size: int = 420) -> float:

@@ -15,13 +15,20 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from foundpose_b200.utils import pnp_util  # noqa: E402
-from oracle import pnp as opnp  # noqa: E402
 
 P, M = 320, 300
+
+
+def rodrigues(w):
+    th = float(np.linalg.norm(w))
+    K = np.array([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]])
+    return np.eye(3) + np.sin(th) / th * K + (1.0 - np.cos(th)) / (th * th) * (K @ K)
+
+
 rng = np.random.default_rng(11)
 X = (rng.normal(size=(P, M, 3)) * 60).astype(np.float32)
 K4 = np.tile(np.array([600.0, 600.0, 210.0, 210.0]), (P, 1))
-Rs = np.stack([opnp.rodrigues(rng.normal(size=3)) for _ in range(P)])
+Rs = np.stack([rodrigues(rng.normal(size=3)) for _ in range(P)])
 ts = np.stack([np.array([rng.uniform(-40, 40), rng.uniform(-40, 40), rng.uniform(500, 900)]) for _ in range(P)])
 Xc = np.einsum("pij,pmj->pmi", Rs, X.astype(np.float64)) + ts[:, None, :]
 x = np.stack([600.0 * Xc[..., 0] / Xc[..., 2] + 210.0, 600.0 * Xc[..., 1] / Xc[..., 2] + 210.0], -1)
