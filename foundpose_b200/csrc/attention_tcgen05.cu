@@ -68,7 +68,7 @@ constexpr uint32_t kKBytes = kBKV * kHD * 2;     // 16 KB
 constexpr uint32_t kVBytes = kBKV * kHD * 2;     // 16 KB
 
 struct AttnBars {
-  uint64_t q_full, q_empty;
+  uint64_t q_full[2], q_empty[2];   // the Q pair of the NEXT item loads while the current one computes
   uint64_t k_full[kKVStages], k_empty[kKVStages];
   uint64_t v_full[kKVStages], v_empty[kKVStages];
   uint64_t s_full[2], s_empty[2], p_full[2], pv_done[2];
@@ -77,7 +77,7 @@ struct AttnBars {
 
 struct AttnSmem {
   static constexpr uint32_t q_off = 0;
-  static constexpr uint32_t k_off = q_off + 2 * kQBytes;
+  static constexpr uint32_t k_off = q_off + 2 * 2 * kQBytes;   // two stages of a Q pair
   static constexpr uint32_t v_off = k_off + kKVStages * kKBytes;
   static constexpr uint32_t max_off = v_off + kKVStages * kVBytes;   // float [2 par][2 tile][2 half][128]
   static constexpr uint32_t sum_off = max_off + 2 * 2 * 2 * kBQ * 4; // float [2 tile][2 half][128]
@@ -342,8 +342,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
-    mbar_init(&bars->q_full, 1);
-    mbar_init(&bars->q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->q_full[s], 1);
+      mbar_init(&bars->q_empty[s], 1);
+    }
     for (int s = 0; s < kKVStages; ++s) {
       mbar_init(&bars->k_full[s], 1);
       mbar_init(&bars->k_empty[s], 1);
@@ -374,19 +376,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t item_phase = 0;
       int dn = 0;
-      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      // Q pair of item number `n` (n-th item of this CTA) goes to Q stage n & 1.
+      auto load_q = [&](int it, int n) {
         const int pair = it % pairs;
         const int head = (it / pairs) % heads;
         const int img = it / (pairs * heads);
-        const int row_base = img * N;
-        mbar_wait(&bars->q_empty, item_phase ^ 1);
+        const int qs = n & 1;
+        mbar_wait(&bars->q_empty[qs], ((n >> 1) & 1) ^ 1);
         dbg_event(dbg, 0, dn, 100);
-        mbar_arrive_expect_tx(&bars->q_full, 2 * kQBytes);
-        tma_load_2d(sQ, &tmQKV, &bars->q_full, head * kHD, row_base + pair * 2 * kBQ);
-        tma_load_2d(sQ + kQBytes, &tmQKV, &bars->q_full, head * kHD, row_base + pair * 2 * kBQ + kBQ);
-        item_phase ^= 1;
+        mbar_arrive_expect_tx(&bars->q_full[qs], 2 * kQBytes);
+        uint8_t* dst = sQ + qs * 2 * kQBytes;
+        tma_load_2d(dst, &tmQKV, &bars->q_full[qs], head * kHD, img * N + pair * 2 * kBQ);
+        tma_load_2d(dst + kQBytes, &tmQKV, &bars->q_full[qs], head * kHD, img * N + pair * 2 * kBQ + kBQ);
+      };
+      int n = 0;
+      if (static_cast<int>(blockIdx.x) < num_items) load_q(blockIdx.x, 0);
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
+        const int head = (it / pairs) % heads;
+        const int img = it / (pairs * heads);
+        const int row_base = img * N;
+        // The next item's Q pair is requested after three K/V blocks of this item: the K/V ring has three
+        // stages, so by then the last S MMA of the previous item - the one that frees that Q stage - has
+        // retired and the request never stalls the K/V stream.
+        const int q_prefetch_at = num_kv < 3 ? num_kv - 1 : 2;
         for (int j = 0; j < num_kv; ++j) {
           mbar_wait(&bars->k_empty[stage], phase ^ 1);
           dbg_event(dbg, 0, dn, 10 + j);
@@ -399,6 +412,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
           tma_load_2d(sV + stage * kVBytes, &tmQKV, &bars->v_full[stage], 2 * D + head * kHD,
                       row_base + j * kBKV);
           if (++stage == kKVStages) { stage = 0; phase ^= 1; }
+          if (j == q_prefetch_at && it + static_cast<int>(gridDim.x) < num_items) load_q(it + gridDim.x, n + 1);
         }
       }
     } else if (warp == 1) {
@@ -413,13 +427,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
       constexpr uint32_t idesc_full = make_idesc_f16(kBQ, kBKV, 0, 0);
       const uint32_t idesc_last = make_idesc_f16(kBQ, last_len, 0, 0);
       int kstage = 0;
-      uint32_t kphase = 0, item_phase = 0;
+      uint32_t kphase = 0;
       uint32_t blk = 0;   // running count of key blocks processed by this CTA (barrier parity)
       int dn = 0;
-      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-        mbar_wait(&bars->q_full, item_phase);
+      int n = 0;          // items done by this CTA: Q stage n & 1, phase (n >> 1) & 1
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
+        const int qs = n & 1;
+        mbar_wait(&bars->q_full[qs], (n >> 1) & 1);
         if (lane == 0) dbg_event(dbg, 1, dn, 100);
-        item_phase ^= 1;
+        const uint64_t qoff = static_cast<uint64_t>(qs * (2 * kQBytes / 16));
         for (int j = 0; j < num_kv; ++j) {
           const uint32_t idesc_s = (j == num_kv - 1) ? idesc_last : idesc_full;
           const uint32_t par = (blk + j) & 1;
@@ -430,7 +446,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
             mbar_wait(&bars->s_empty[x], par ^ 1);
             tc_fence_after_sync();
             if (elect_one()) {
-              const uint64_t qd = x == 0 ? qdesc0 : qdesc1;
+              const uint64_t qd = (x == 0 ? qdesc0 : qdesc1) + qoff;
 #pragma unroll
               for (int k = 0; k < kHD / 16; ++k)
                 umma_f16_ss(tmem_base + kColS + x * kBKV, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
@@ -441,7 +457,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
           }
           if (elect_one()) {
             umma_commit(&bars->k_empty[kstage]);
-            if (j == num_kv - 1) umma_commit(&bars->q_empty);   // Q tiles may be overwritten
+            if (j == num_kv - 1) umma_commit(&bars->q_empty[qs]);   // this Q stage may be overwritten
           }
           __syncwarp();
           if (++kstage == kKVStages) { kstage = 0; kphase ^= 1; }
