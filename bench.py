@@ -34,6 +34,12 @@ WORKLOADS = {
                     desc="configs[1]: batch=64 synthetic 420x420 crops, ViT-L/14 layer 9 + PCA 1024->256 + "
                          "tf-idf top-5 template retrieval + cyclic buddies vs 2000-template x 1024-patch x "
                          "256-d bank"),
+    # BASELINE.json configs[3] - LM-O-shaped bank of ONE object (the 8 objects are 8 such banks processed one after the
+    # other, scripts/infer.py:207 loops over objects); crops shard over the GPUs exactly as in config2.
+    "config4": dict(batch=64, vit="dinov2_vitl14", templates=800, patches=1200, dim=384, pca=True,
+                    words=2048, top_n=5, top_k=300,
+                    desc="configs[3] (one object): batch=64 synthetic 420x420 crops per GPU, ViT-L/14 layer 9 + PCA "
+                         "1024->384 + tf-idf top-5 retrieval + cyclic buddies vs 800-template x 1200-patch x 384-d bank"),
     # Small variant for quick functional checks of bench.py itself (not a reported configuration).
     "tiny": dict(batch=8, vit="dinov2_version=vits14-reg_stride=14_facet=token_layer=9_norm=1", templates=64,
                  patches=256, dim=256, pca=True, words=256, top_n=5, top_k=300,
