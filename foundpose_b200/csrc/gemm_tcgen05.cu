@@ -46,23 +46,25 @@ __device__ __forceinline__ float gelu_erf_libm(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
-// Same function with erf evaluated by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7 plus the
-// approximate reciprocal / exp2, together < 1e-6: far below the fp16 rounding of the stored
-// activation).  ~14 FP32 ops + 2 MUFU per element instead of erff()'s branchy ~50.
+// Same function through erfc(z) = 2^P(z), z = |x| / sqrt(2), P a degree-5 polynomial without constant term
+// fitted (minimax in erfc) on [0, 4.3]: max abs error 6e-7 in erf - the class of Abramowitz-Stegun 7.1.26 and
+// far below the fp16 rounding of the stored activation - with ONE MUFU (ex2) and 10 FP32 ops per element
+// (A-S 7.1.26 needs rcp + ex2 and 13; erff() ~50 with branches).  The leading coefficient is negative, so
+// 2^P -> 0 for large |x| without a clamp.  It matters because the epilogue of a 128x256 tile shares its SM
+// sub-partitions with nothing else but must finish within the 8192 cycles the tile's MMAs take: at 2 MUFU +
+// 13 FMA per element the fc1 kernel ran at 72% tensor-pipe activity against 85% for the qkv kernel
+// (profiles/r01_final_summary.md).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;   // exp(-z^2) = exp2(-z^2 * log2(e))
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x| / sqrt(2))
+  float p = fmaf(-0.002944134408608079f, z, 0.029589958488941193f);
+  p = fmaf(p, z, -0.14866553246974945f);
+  p = fmaf(p, z, -0.9185094237327576f);
+  p = fmaf(p, z, -1.6278890371322632f);
+  p *= z;
+  float e;   // erfc(z)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
   const float half_x = 0.5f * x;
-  return fmaf(half_x, copysignf(erf_abs, x), half_x);  // 0.5 x (1 + erf(x / sqrt(2)))
+  return fmaf(fabsf(half_x), 1.0f - e, half_x);   // 0.5 x (1 + sign(x) erf(z))
 }
 
 template <int EPI>
