@@ -8,6 +8,8 @@ the search is `fp_knn_search_items` (tcgen05 distance tiles + register top-k).  
 on the device of the query tensor, as the reference does (:102-104).
 """
 
+import math
+import os
 from typing import Any, Optional, Tuple
 
 import torch
@@ -17,7 +19,20 @@ from foundpose_b200 import _native
 _MAX_K = 16
 _SPLIT_BELOW_ITEMS = 74     # fewer query blocks than half the SMs -> split the bank
 _SPLIT_MIN_ROWS = 16384
-_TARGET_ITEMS = 592         # 148 SMs x 4 items
+_NUM_SMS = 148
+_TARGET_ITEMS = int(os.environ.get("FOUNDPOSE_KNN_TARGET_ITEMS", "592"))   # upper bound on items of a split search
+
+
+def _choose_num_chunks(n_q: int) -> int:
+    """Bank chunks per query block for the split path: the fewest chunks whose n_q x chunks items fill whole
+    waves of the 148 persistent CTAs (every extra item per SM costs a pipeline restart and a merge: one chunk per
+    SM reached 57-88% of the HBM peak on 0.8-7.9 GB banks where four reached 45-75%)."""
+    effs = []
+    for c in range(1, max(1, _TARGET_ITEMS // n_q) + 1):
+        waves = n_q * c / _NUM_SMS
+        effs.append(waves / math.ceil(waves))
+    best = max(effs)
+    return 1 + next(i for i, e in enumerate(effs) if e >= best - 0.03)
 
 
 def _device_for(t: torch.Tensor) -> torch.device:
@@ -92,7 +107,7 @@ class KNN:
             # Few query blocks against a large bank: split the bank so that all SMs stream it.
             num_chunks = 1
             if n_q < _SPLIT_BELOW_ITEMS and nb >= _SPLIT_MIN_ROWS:
-                want = max(1, _TARGET_ITEMS // n_q)
+                want = _choose_num_chunks(n_q)
                 chunk_rows = max(256, ((nb + want - 1) // want + 255) // 256 * 256)
                 num_chunks = (nb + chunk_rows - 1) // chunk_rows
             if num_chunks > 1:
