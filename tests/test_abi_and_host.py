@@ -174,3 +174,17 @@ def test_cpu_inputs_are_rejected_by_every_entry_point():
         proj.transform(torch.zeros(3, 128))
     with pytest.raises(ValueError):
         template_util.calc_tfidf(torch.zeros(3, 3, dtype=torch.int64), torch.zeros(3, 3), torch.ones(8), False)
+
+
+def test_knn_split_chunk_count_fills_whole_waves():
+    """Host logic of the split k-NN path: the fewest bank chunks whose items fill whole waves of the 148 CTAs."""
+    import math
+
+    from foundpose_b200.utils import knn_util
+
+    assert knn_util._choose_num_chunks(1) in range(141, 149)          # one chunk per SM for a single query block
+    for n_q in (1, 2, 3, 8, 37, 57, 73):
+        c = knn_util._choose_num_chunks(n_q)
+        waves = n_q * c / 148
+        assert 1 <= c <= max(1, 592 // n_q)
+        assert waves / math.ceil(waves) >= 0.93, (n_q, c)
