@@ -212,7 +212,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def self_depth(path: CpuReferencePath) -> int:
@@ -478,7 +478,7 @@ def run_cuda_arm(args) -> None:
             "cpu_baseline": cpu_baseline,
         }
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         import torch.distributed as dist
 
@@ -562,7 +562,26 @@ def vit_flops_per_crop(arch, layer: int, size: int = 420) -> float:
     return float(patch + (layer + 1) * block)
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the
+    first collective), so everything but the result line is routed to stderr at the file-descriptor level."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit_line(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main() -> None:
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
