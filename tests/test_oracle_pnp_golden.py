@@ -69,3 +69,30 @@ def test_too_few_points_and_iteration_budget():
     assert opnp.ransac_update_num_iters(0.99, 0.5, 4, 400) == 71
     assert opnp.ransac_update_num_iters(0.99, 0.0, 4, 400) == 0
     assert opnp.ransac_update_num_iters(0.99, 1.0, 4, 400) == 400
+
+
+def test_refine_lm_converges_from_a_perturbed_pose():
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(40, 3)) * 50
+    R = opnp.rodrigues(np.array([0.2, -0.4, 0.1]))
+    t = np.array([10.0, -5.0, 700.0])
+    K4 = np.array([600.0, 590.0, 210.0, 205.0])
+    Xc = X @ R.T + t
+    x = np.stack([K4[0] * Xc[:, 0] / Xc[:, 2] + K4[2], K4[1] * Xc[:, 1] / Xc[:, 2] + K4[3]], 1)
+    R0 = opnp.rodrigues(np.array([0.03, -0.02, 0.04])) @ R
+    t0 = t + np.array([3.0, -2.0, 15.0])
+    R1, t1 = opnp.refine_lm(R0, t0, K4, X, x)
+    assert np.abs(R1 - R).max() < 1e-8 and np.abs(t1 - t).max() < 1e-5
+    assert np.abs(R1 @ R1.T - np.eye(3)).max() < 1e-12
+
+
+def test_select_best_poses_host_logic():
+    import torch
+
+    from foundpose_b200.utils import pnp_util
+
+    success = torch.tensor([1, 1, 1, 0, 0, 0, 1, 0, 1], dtype=torch.int32)
+    inliers = torch.tensor([12, 40, 40, 99, 0, 0, 7, 50, 7], dtype=torch.int32)
+    best = pnp_util.select_best_poses(success, inliers, 3)
+    # first maximal quality wins (scripts/infer.py:592-603); failed problems never win; no success -> -1
+    assert best.tolist() == [1, -1, 0]
