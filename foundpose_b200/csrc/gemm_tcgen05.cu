@@ -421,10 +421,12 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* ld_bar = tempty_bar + 3;              // residual read-modify-write mode: 2 per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();        // 0 = leader (issues the MMAs)
+  const bool resid_rmw = Cfg::kTmaReduce && (p.flags & 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -436,6 +438,9 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);                // multicast tcgen05.commit
       mbar_init(&tempty_bar[a], 2 * kEpilogueWarps);   // leader: epilogue warps of both CTAs
+    }
+    if constexpr (Cfg::kTmaReduce) {
+      for (int i = 0; i < 2 * kEpilogueWarps; ++i) mbar_init(&ld_bar[i], 1);
     }
     fence_barrier_init();
   } else if (warp == 2) {
@@ -509,11 +514,25 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t ld_phase[2] = {0, 0};
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int m_blk = t / num_n;
       const int n_blk = t - m_blk * num_n;
       const int row0 = m_blk * 2 * BM + static_cast<int>(rank) * BM + sub * 32;
       const int row = row0 + lane;
+      if constexpr (Cfg::kTmaReduce) {
+        // Read-modify-write mode: the x blocks of the first two chunks are requested while the tile's MMAs run.
+        if (resid_rmw && lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (c == 0) tma_store_wait_read<1>(); else tma_store_wait_read<0>();   // the store that last read it
+            uint8_t* buf = staging + (warp - 4) * 8192 + c * 4096;
+            uint64_t* bar = &ld_bar[(warp - 4) * 2 + c];
+            mbar_arrive_expect_tx(bar, 4096);
+            tma_load_2d(buf, &tmC, bar, n_blk * BN + half * (BN / 2) + c * 32, row0);
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
@@ -576,6 +595,36 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // y = gamma * (acc + bias) -> 128B-swizzled 32 x 32 fp32 block in smem -> TMA reduce-add.
           const int n0 = n_blk * BN + col0;
           uint8_t* buf = staging + (warp - 4) * 8192 + (c & 1) * 4096;
+          if (resid_rmw) {
+            // Alternative: x block fetched by the TMA (requested two chunks ahead), x += y in shared memory,
+            // plain TMA store - same HBM traffic as the reduce-add, none of its L2 atomics.
+            mbar_wait(&ld_bar[(warp - 4) * 2 + (c & 1)], ld_phase[c & 1]);
+            ld_phase[c & 1] ^= 1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j * 4));
+              float4* cell = reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4));
+              float4 y = *cell;
+              y.x += g.x * (__uint_as_float(r[j * 4 + 0]) + b.x);
+              y.y += g.y * (__uint_as_float(r[j * 4 + 1]) + b.y);
+              y.z += g.z * (__uint_as_float(r[j * 4 + 2]) + b.z);
+              y.w += g.w * (__uint_as_float(r[j * 4 + 3]) + b.w);
+              *cell = y;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, buf, n0, row0);
+              tma_store_commit();
+              if (c + 2 < BN / 64) {   // request the x block of chunk c + 2 into the buffer just stored from
+                tma_store_wait_read<0>();
+                uint64_t* bar = &ld_bar[(warp - 4) * 2 + (c & 1)];
+                mbar_arrive_expect_tx(bar, 4096);
+                tma_load_2d(buf, &tmC, bar, n0 + 64, row0);
+              }
+            }
+          } else {
           if (lane == 0) tma_store_wait_read<1>();   // the store that last read this buffer is done
           __syncwarp();
 #pragma unroll
@@ -594,6 +643,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) {
             tma_reduce_add_2d(&tmC, buf, n0, row0);
             tma_store_commit();
+          }
           }
         } else {
           if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r);
