@@ -103,3 +103,32 @@ def test_gemm_throughput_report():
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / iters
         print(f"  cuBLAS fp16 same shape: {ms:.3f} ms  {2.0 * m * n * k / ms / 1e9:.1f} TFLOP/s")
+
+
+def test_residual_epilogue_modes_agree():
+    """The two residual epilogues (TMA reduce-add through the L2 vs TMA load + add + store) compute the same
+    x += gamma * (A B^T + bias); they differ by at most the rounding of one fused multiply-add."""
+    import ctypes
+
+    from foundpose_b200 import _native
+
+    lib = _native.load()
+    m, n, k = 3000, 512, 256            # pair kernel (N % 256 == 0, M > 256), ragged last row tile
+    a, b = _rand((m, k), 21), _rand((n, k), 22, 0.05)
+    bias = torch.randn(n, generator=torch.Generator().manual_seed(23)).cuda()
+    gamma = torch.randn(n, generator=torch.Generator().manual_seed(24)).cuda()
+    x0 = torch.randn(m, n, generator=torch.Generator().manual_seed(25)).cuda()
+    outs = []
+    try:
+        for mode in (0, 1):
+            lib.fp_gemm_force_1sm(ctypes.c_int(mode << 1))
+            x = x0.clone()
+            _native.gemm_tn_f16(a, b, _native.EPI_RESID_F32, bias=bias, gamma=gamma, out_f32=x)
+            torch.cuda.synchronize()
+            outs.append(x)
+    finally:
+        lib.fp_gemm_force_1sm(ctypes.c_int(0))
+    ref = x0 + gamma * (a.float() @ b.float().t() + bias)
+    assert (outs[0] - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    assert (outs[1] - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    assert (outs[0] - outs[1]).abs().max().item() <= 4e-6 * ref.abs().max().item()
