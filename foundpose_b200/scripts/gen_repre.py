@@ -10,7 +10,8 @@ the same calls in the same order and the same output container:
 
   * feature extraction: ONE batched extractor call per chunk of templates (the reference: one call per
     template), `feature_util.get_visual_features_registered_in_3d` for the 3D registration;
-  * PCA fit: scikit-learn like the reference (`projector_util.PCAProjector.fit`), transform on the GPU;
+  * PCA fit: covariance on the tcgen05 GEMM + eigendecomposition (`projector_util.PCAProjector.fit`, scikit-learn's
+    `covariance_eigh` conventions), transform on the GPU;
   * k-means: `cluster_util.kmeans` (tcgen05 assignment + fixed-point update kernels);
   * tf-idf descriptors: `template_util.calc_tfidf_descriptors`;
   * `repre_util.save_object_repre`: the reference's `repre.pth` layout.

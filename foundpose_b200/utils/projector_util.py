@@ -49,16 +49,64 @@ class PCAProjector(Projector):
         self._device_state: Dict[str, Dict[str, torch.Tensor]] = {}
 
     def fit(self, data_x: torch.Tensor, data_y: Optional[torch.Tensor] = None, **kwargs: Any) -> None:
-        """Offline (scripts/gen_repre.py:272-284): delegated to scikit-learn like the reference."""
-        from sklearn.decomposition import PCA
+        """PCA fit of the offline bank build (reference utils/projector_util.py:53-64, scripts/gen_repre.py:272-284).
 
+        CUDA tensors are fitted on the GPU with the algorithm scikit-learn itself calls "covariance_eigh"
+        (sklearn/decomposition/_pca.py, chosen by `PCA(...)` for tall data): covariance of the centred samples,
+        symmetric eigendecomposition, eigenvectors flipped so that the largest entry of every component is positive
+        (`svd_flip(u_based_decision=False)`).  The covariance - the O(n D^2) part - runs on the tcgen05 GEMM with the
+        fp32 samples split into two fp16 terms (x = hi + lo, the lo.lo product is below fp32 resolution); the D x D
+        eigendecomposition is cuSOLVER's through torch.linalg.eigh (float64).  CPU tensors go to scikit-learn exactly
+        as the reference does.
+        """
         if "max_samples" in kwargs:
             if data_x.shape[0] > kwargs["max_samples"]:
                 perm = torch.randperm(data_x.shape[0])
-                data_x = data_x[perm[: kwargs["max_samples"]]]
-        self.pca = PCA(n_components=self.n_components, whiten=self.whiten)
-        self.pca.fit(tensor_to_array(data_x))
+                data_x = data_x[perm[: kwargs["max_samples"]].to(data_x.device)]
         self._device_state = {}
+        if not data_x.is_cuda:
+            from sklearn.decomposition import PCA
+
+            self.pca = PCA(n_components=self.n_components, whiten=self.whiten)
+            self.pca.fit(tensor_to_array(data_x))
+            return
+        x = data_x.detach().to(torch.float32)
+        n, d = x.shape
+        if not 1 <= self.n_components <= min(n, d):
+            raise ValueError(f"n_components={self.n_components} must be between 1 and min(n_samples, n_features)="
+                             f"{min(n, d)}")
+        mean = x.mean(dim=0)
+        d_pad = (d + 127) // 128 * 128
+        n_pad = (n + 63) // 64 * 64
+        xt = torch.zeros((d_pad, n_pad), dtype=torch.float32, device=x.device)      # [features, samples]
+        xt[:d, :n] = (x - mean).t()
+        hi = xt.to(torch.float16)
+        lo = (xt - hi.to(torch.float32)).to(torch.float16)
+        zero_bias = torch.zeros(d_pad, dtype=torch.float32, device=x.device)
+        g_hh = torch.empty((d_pad, d_pad), dtype=torch.float32, device=x.device)
+        g_hl = torch.empty((d_pad, d_pad), dtype=torch.float32, device=x.device)
+        _native.gemm_tn_f16(hi, hi, _native.EPI_BIAS_F32, bias=zero_bias, out_f32=g_hh)
+        _native.gemm_tn_f16(hi, lo, _native.EPI_BIAS_F32, bias=zero_bias, out_f32=g_hl)
+        cov = (g_hh + g_hl + g_hl.t())[:d, :d].to(torch.float64)
+        cov = 0.5 * (cov + cov.t()) / (n - 1)
+        eigenvals, eigenvecs = torch.linalg.eigh(cov)
+        eigenvals = torch.flip(eigenvals, dims=(0,)).clamp_min(0.0)
+        vt = torch.flip(eigenvecs, dims=(1,)).t()                                   # rows = components
+        # svd_flip(u_based_decision=False): the entry of largest magnitude of every row becomes positive
+        idx = vt.abs().argmax(dim=1)
+        signs = torch.sign(vt[torch.arange(vt.shape[0], device=vt.device), idx])
+        signs[signs == 0] = 1.0
+        vt = vt * signs[:, None]
+        k = self.n_components
+        state = _PCAState(n_components=k, whiten=self.whiten)
+        state.components_ = vt[:k].to(torch.float32).cpu().numpy()
+        state.mean_ = mean.cpu().numpy()
+        state.explained_variance_ = eigenvals[:k].to(torch.float32).cpu().numpy()
+        state.explained_variance_ratio_ = (eigenvals[:k] / eigenvals.sum()).to(torch.float32).cpu().numpy()
+        state.singular_values_ = torch.sqrt(eigenvals[:k] * (n - 1)).to(torch.float32).cpu().numpy()
+        state.noise_variance_ = float(eigenvals[k:].mean()) if k < min(n, d) else 0.0
+        state.n_samples_, state.n_features_in_ = n, d
+        self.pca = state
 
     def device_state(self, device: torch.device) -> Dict[str, torch.Tensor]:
         """fp16 components (rows padded to a multiple of 128) and the fused bias on `device`."""

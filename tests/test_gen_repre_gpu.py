@@ -122,3 +122,40 @@ def test_generate_repre_round_trip_and_self_retrieval(tmp_path):
             mine = loaded.vertices.cpu()[(loaded.feat_to_template_ids.cpu() == t)]
             assert torch.allclose(corresp[0]["coord_3d"].cpu(), mine[corresp[0]["coord_2d_ids"].cpu()], atol=1e-4)
     assert hits >= 7                                                        # 8 probes
+
+
+@pytest.mark.parametrize("n,d,k", [(3000, 256, 64), (1111, 200, 16)])
+def test_pca_fit_gpu_matches_sklearn(n, d, k):
+    """PCAProjector.fit on CUDA data (tcgen05 covariance + eigh) against scikit-learn's exact solver."""
+    from sklearn.decomposition import PCA
+
+    from foundpose_b200.utils import projector_util
+    g = torch.Generator().manual_seed(7)
+    scales = torch.linspace(6.0, 1.0, 32)                       # 32 well separated directions + isotropic noise
+    x = (torch.randn(n, 32, generator=g) * scales) @ torch.linalg.qr(torch.randn(d, 32, generator=g))[0].t()
+    x = x + 0.05 * torch.randn(n, d, generator=g) + 3.0 * torch.randn(1, d, generator=g)
+    proj = projector_util.PCAProjector(n_components=k)
+    proj.fit(x.cuda())
+    ref = PCA(n_components=k, svd_solver="full").fit(x.numpy())
+    assert proj.pca.components_.shape == (k, d) and proj.pca.mean_.shape == (d,)
+    assert np.allclose(proj.pca.mean_, ref.mean_, atol=1e-5)
+    # eigenvalues agree to fp32 resolution of the LARGEST one (the covariance is accumulated in fp32): the 32 signal
+    # eigenvalues to ~1e-5 relative, the noise floor (1e-4 of the top) to a fraction of a percent
+    ev0 = float(ref.explained_variance_[0])
+    assert np.allclose(proj.pca.explained_variance_, ref.explained_variance_, rtol=1e-4, atol=3e-6 * ev0)
+    assert np.allclose(proj.pca.explained_variance_ratio_, ref.explained_variance_ratio_, rtol=1e-4,
+                       atol=3e-6 * float(ref.explained_variance_ratio_[0]))
+    assert np.allclose(proj.pca.singular_values_ ** 2 / (n - 1), proj.pca.explained_variance_, rtol=1e-5)
+    assert np.allclose(proj.pca.singular_values_[:16], ref.singular_values_[:16], rtol=1e-4)
+    assert abs(proj.pca.noise_variance_ - ref.noise_variance_) <= 2e-2 * ref.noise_variance_
+    top = min(k, 32)                                            # the separated directions: same vectors, same signs
+    dots = (proj.pca.components_[:top] * ref.components_[:top]).sum(1)
+    assert dots.min() > 0.999
+    # the projector is usable as fitted: transform == sklearn's transform on the separated directions
+    if d % 64 == 0:       # the projection kernel takes feature widths that are multiples of 64 (all DINOv2 widths)
+        mine = proj.transform(x.cuda()).cpu().numpy()[:, :top]
+        theirs = ref.transform(x.numpy())[:, :top]
+        assert np.abs(mine - theirs).max() <= 5e-3 * np.abs(theirs).max()
+    # tensordict round trip (repre.pth layout)
+    again = projector_util.projector_from_tensordict(projector_util.projector_to_tensordict(proj))
+    assert np.array_equal(again.pca.components_, proj.pca.components_)
