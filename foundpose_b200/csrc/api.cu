@@ -24,6 +24,19 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int num_sms() {
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // ---- launch accounting / profiling --------------------------------------------------------
 struct ProfRecord {
   int category;
@@ -65,6 +78,8 @@ ProfScope::~ProfScope() {
 extern "C" {
 
 unsigned long long fp_launch_count(void) { return fp::g_launches.load(); }
+
+int fp_num_sms(void) { return fp::num_sms(); }
 
 unsigned long long fp_launch_count_category(int category) {
   if (category < 0 || category >= fp::PROF_NUM_CATEGORIES) return 0;
@@ -218,6 +233,21 @@ int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_
                               reinterpret_cast<const fp::KnnItem*>(items), num_items, q_sqnorm,
                               bank_sqnorm, metric, k, out_d, out_i,
                               static_cast<cudaStream_t>(stream));
+}
+
+int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const float* q_sqnorm,
+                             const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
+                             int dim, const fp_knn_item* items, int num_items, int metric, int k,
+                             float* out_d, int64_t* out_i, void* stream) {
+  if (metric != 0 && metric != 1) {
+    fp::set_last_error("Metric %d is not supported.", metric);
+    return 1;
+  }
+  return fp::knn_search_pair_items(static_cast<const __half*>(q_f16), q_rows_total,
+                                   static_cast<const __half*>(bank_f16), bank_rows_total, dim,
+                                   reinterpret_cast<const fp::KnnItem*>(items), num_items, q_sqnorm,
+                                   bank_sqnorm, metric, k, out_d, out_i,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int fp_crop_warp(const void* images, int src_is_f32, int num_images, int src_h, int src_w,

@@ -618,7 +618,7 @@ int attention_f16(const __half* qkv, __half* out, int B, int N, int heads, cudaS
   if (make_tma_2d_f16(&tm, qkv, static_cast<uint64_t>(B) * N, 3ull * D, 3ull * D, kBQ) != 0) return 3;
   const int pairs = (N + 2 * kBQ - 1) / (2 * kBQ);
   const int num_items = pairs * heads * B;
-  const int grid = num_items < kNumSMs ? num_items : kNumSMs;
+  const int grid = num_items < num_sms() ? num_items : num_sms();
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // hd^-0.5 * log2(e), hd = 64
   ProfScope prof(PROF_ATTENTION, stream, 4.0 * B * heads * static_cast<double>(N) * N * kHD);
   // Kernel variants: (threads per row, share of the exponentials of tile A / tile B evaluated on

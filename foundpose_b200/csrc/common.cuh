@@ -13,7 +13,9 @@
 
 namespace fp {
 
-constexpr int kNumSMs = 148;
+// SM count of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a B200).
+// Persistent grids and grid caps are sized from it.
+int num_sms();
 
 // ----------------------------------------------------------------------------
 // Error plumbing shared by all translation units (defined in api.cu).
@@ -52,7 +54,8 @@ enum ProfCategory : int {
   PROF_KNN = 4,         // knn_kernel              (work = flops, upper bound for device-built items)
   PROF_FEATURE = 5,     // mask filter, sampling, conversions, norms (work = bytes)
   PROF_RETRIEVAL = 6,   // tf-idf, cosine scores, top-k, items, cyclic buddies (work = bytes)
-  PROF_NUM_CATEGORIES = 7,
+  PROF_KNN_PAIR = 7,    // knn_pair_kernel: tensor-bound full-bank search (work = 0, the caller knows the flops)
+  PROF_NUM_CATEGORIES = 8,
 };
 
 struct ProfScope {
@@ -276,6 +279,72 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// cta_group::2 (a cluster of two CTAs on one TPC sharing one MMA): cluster helpers, TMEM allocation,
+// TMA loads that complete on the leader's barrier, the paired MMA and its multicast commit.
+// ----------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the leader's copy
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// TMA load into this CTA's smem, completing on the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all prior MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 0x3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :
+      : "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// Arrive on the leader CTA's copy of a barrier (local arrive when executed by the leader).
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) &
+                                                                                   kPeerBitMask)
+               : "memory");
 }
 
 // ----------------------------------------------------------------------------

@@ -155,7 +155,7 @@ int sample_features(const float* tokens, int B, int Hp, int Wp, int C, const flo
   const long total = static_cast<long>(B) * stride;
   if (total <= 0) return 0;
   long blocks = (total + 7) / 8;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   ProfScope prof(PROF_FEATURE, stream, static_cast<double>(total) * C * (4 + (out_f32 ? 4 : 0) + (out_f16 ? 2 : 0)));
   sample_features_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
       tokens, Hp, Wp, C, points, counts, stride, B, img_w, img_h, out_f32, out_f16);

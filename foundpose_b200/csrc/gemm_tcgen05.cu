@@ -301,68 +301,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // profiles/r01_baseline_summary.md).  Only the leader CTA issues MMAs; completion is multicast to
 // both CTAs' barriers; both CTAs run their own TMA producer and epilogue warps.
 // ----------------------------------------------------------------------------------------
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the leader's copy
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   smem_u32(smem_dst)),
-               "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish_2sm() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-               : "memory");
-}
-// TMA load into this CTA's smem, completing on the LEADER CTA's mbarrier.
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
-                                                int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                                uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n"
-      :
-      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Arrive (once all prior MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair.
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-  const uint16_t mask = 0x3;
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      :
-      : "r"(smem_u32(bar)), "h"(mask)
-      : "memory");
-}
-// Arrive on the leader CTA's copy of a barrier (local arrive when executed by the leader).
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) &
-                                                                                   kPeerBitMask)
-               : "memory");
-}
-
 template <int EPI>
 struct Gemm2Cfg {
   // The residual epilogue stages its output through shared memory for TMA reduce-add stores
@@ -688,7 +626,7 @@ int launch_2sm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
                                        Cfg::kSmemBytes));
   }
   const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / Cfg::BN);
-  int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
+  int clusters = num_tiles < num_sms() / 2 ? num_tiles : num_sms() / 2;
   ProfScope prof(PROF_GEMM, stream, 2.0 * p.M * p.N * p.K);
   gemm2_tn_kernel<EPI><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   FP_CUDA_CHECK(cudaGetLastError());
@@ -706,7 +644,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
                                        Cfg::kSmemBytes));
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   ProfScope prof(PROF_GEMM, stream, 2.0 * p.M * p.N * p.K);
   gemm_tn_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   FP_CUDA_CHECK(cudaGetLastError());
@@ -734,11 +672,11 @@ int gemm_pick_bn(int M, int N) {
   if (N % 256 != 0) return 128;
   // Prefer the 128x256 tile unless it quantises badly onto 148 SMs.
   const long tiles256 = static_cast<long>((M + BM - 1) / BM) * (N / 256);
-  const long waves256 = (tiles256 + kNumSMs - 1) / kNumSMs;
-  const double eff256 = static_cast<double>(tiles256) / (waves256 * kNumSMs);
+  const long waves256 = (tiles256 + num_sms() - 1) / num_sms();
+  const double eff256 = static_cast<double>(tiles256) / (waves256 * num_sms());
   const long tiles128 = tiles256 * 2;
-  const long waves128 = (tiles128 + kNumSMs - 1) / kNumSMs;
-  const double eff128 = static_cast<double>(tiles128) / (waves128 * kNumSMs);
+  const long waves128 = (tiles128 + num_sms() - 1) / num_sms();
+  const double eff128 = static_cast<double>(tiles128) / (waves128 * num_sms());
   return (eff128 > eff256 + 0.04) ? 128 : 256;
 }
 

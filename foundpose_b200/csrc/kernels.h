@@ -84,6 +84,12 @@ int knn_search_items(const __half* q, long q_rows_total, const __half* x, long x
                      int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream);
 
 
+// Pair kernel (cta_group::2, queries resident in shared memory): items hold up to 256 query rows.
+int knn_search_pair_items(const __half* q, long q_rows_total, const __half* x, long x_rows_total, int dim,
+                          const KnnItem* items, int num_items, const float* qnorm, const float* xnorm,
+                          int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream);
+
+
 // ---- crop_warp.cu -----------------------------------------------------------------------
 int crop_warp(const void* images, int src_is_f32, int num_images, int src_h, int src_w, int channels,
               const uint8_t* masks, const double* params, int B, int crop_w, int crop_h,

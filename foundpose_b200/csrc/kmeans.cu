@@ -54,7 +54,7 @@ int kmeans_update(const float* x, const int64_t* assign, long long n, int d, int
   FP_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * static_cast<size_t>(k) * d, stream));
   FP_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(int) * static_cast<size_t>(k), stream));
   if (n > 0) {
-    const long long want = n < static_cast<long long>(kNumSMs) * 16 ? n : static_cast<long long>(kNumSMs) * 16;
+    const long long want = n < static_cast<long long>(num_sms()) * 16 ? n : static_cast<long long>(num_sms()) * 16;
     ProfScope prof(PROF_FEATURE, stream, static_cast<double>(n) * d * 4.0);
     kmeans_accumulate_kernel<<<static_cast<unsigned>(want), 256, 0, stream>>>(x, assign, n, d, k, sums, counts);
     FP_CUDA_CHECK(cudaGetLastError());

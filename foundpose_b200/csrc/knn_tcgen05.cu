@@ -73,6 +73,126 @@ struct TopK {
   }
 };
 
+
+// One epilogue thread's share of a 128 x 256 distance tile: its query row (TMEM lane) x one half (128) of the
+// tile's bank columns, starting at TMEM address `taddr`.  `ncols` = valid columns in this half (may be <= 0),
+// `xn` = ||x||^2 of the half's first column, `col_base` = index of that column relative to the item's segment.
+// L2: ||x||^2 - 2<q,x> (||q||^2 is added once per item); IP: -<q,x>.
+template <int K>
+__device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, const float* __restrict__ xn,
+                                               int col_base, int metric_ip, TopK<K>& best) {
+  // 16-byte loads of the bank norms when the segment start allows it (always for full-bank searches).
+  const bool xn_vec = (reinterpret_cast<uintptr_t>(xn) & 15) == 0;
+#pragma unroll 1
+  for (int c = 0; c < BX / 64; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    if (c * 32 < ncols) {
+      float dist[32];
+      if (c * 32 + 32 <= ncols) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!metric_ip) {
+            if (xn_vec) {
+              n4 = __ldg(reinterpret_cast<const float4*>(xn + c * 32 + g * 4));
+            } else {
+              n4.x = __ldg(xn + c * 32 + g * 4 + 0); n4.y = __ldg(xn + c * 32 + g * 4 + 1);
+              n4.z = __ldg(xn + c * 32 + g * 4 + 2); n4.w = __ldg(xn + c * 32 + g * 4 + 3);
+            }
+          }
+          dist[g * 4 + 0] = metric_ip ? -__uint_as_float(v[g * 4 + 0]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 0]), n4.x);
+          dist[g * 4 + 1] = metric_ip ? -__uint_as_float(v[g * 4 + 1]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 1]), n4.y);
+          dist[g * 4 + 2] = metric_ip ? -__uint_as_float(v[g * 4 + 2]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 2]), n4.z);
+          dist[g * 4 + 3] = metric_ip ? -__uint_as_float(v[g * 4 + 3]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 3]), n4.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = c * 32 + i;
+          float dv = INFINITY;
+          if (col < ncols) {
+            const float dot = __uint_as_float(v[i]);
+            dv = metric_ip ? -dot : fmaf(-2.0f, dot, __ldg(xn + col));
+          }
+          dist[i] = dv;
+        }
+      }
+      if constexpr (K == 1) {
+        // argmin of the 32 candidates by a tree (depth 5) instead of a 32-deep serial chain;
+        // the left operand (lower index) wins ties.
+        int idx[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool lt = dist[2 * i + 1] < dist[2 * i];
+          dist[i] = lt ? dist[2 * i + 1] : dist[2 * i];
+          idx[i] = lt ? 2 * i + 1 : 2 * i;
+        }
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            const bool lt = dist[2 * i + 1] < dist[2 * i];
+            dist[i] = lt ? dist[2 * i + 1] : dist[2 * i];
+            idx[i] = lt ? idx[2 * i + 1] : idx[2 * i];
+          }
+        }
+        if (dist[0] < best.d[0]) {
+          best.d[0] = dist[0];
+          best.i[0] = col_base + c * 32 + idx[0];
+        }
+      } else {
+        // Cheap prefilter: skip the chunk when nothing beats the current k-th best.
+        float cmin = dist[0];
+#pragma unroll
+        for (int i = 1; i < 32; ++i) cmin = fminf(cmin, dist[i]);
+        if (cmin < best.d[K - 1]) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) best.push(dist[i], col_base + c * 32 + i);
+        }
+      }
+    }
+  }
+}
+
+// Merges the two column halves of an item through shared memory (their index ranges interleave tile by tile ->
+// lexicographic order) and writes the k_out best of query row `r` (valid iff r < q_rows).  All 256 epilogue
+// threads of the CTA call it.
+template <int K>
+__device__ __forceinline__ void merge_halves_and_store(TopK<K>& best, int half, int r, int q_rows, long out_row,
+                                                       float qn, int metric_ip, int k_out, uint8_t* merge_buf,
+                                                       float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  float* merge_d = reinterpret_cast<float*>(merge_buf);
+  int* merge_i = reinterpret_cast<int*>(merge_buf + BQ * kMaxK * 4);
+  if (half == 1) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      merge_d[j * BQ + r] = best.d[j];
+      merge_i[j * BQ + r] = best.i[j];
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (half == 0) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) best.push_lex(merge_d[j * BQ + r], merge_i[j * BQ + r]);
+    if (r < q_rows) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (j < k_out) {
+          float dv;
+          if (metric_ip) dv = -best.d[j];                 // similarity, descending
+          else dv = fmaxf(best.d[j] + qn, 0.f);           // faiss clamps negative distances to 0
+          if (best.i[j] < 0) dv = metric_ip ? -INFINITY : INFINITY;  // fewer than k bank rows
+          out_d[out_row * k_out + j] = dv;
+          out_i[out_row * k_out + j] = best.i[j];
+        }
+      }
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");   // merge buffer reusable
+}
+
 template <int K>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
@@ -177,8 +297,6 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const int half = (warp - 4) >> 2;
     const int r = sub * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
-    float* merge_d = reinterpret_cast<float*>(merge_buf);
-    int* merge_i = reinterpret_cast<int*>(merge_buf + BQ * kMaxK * 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
@@ -191,112 +309,17 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
-        const int ncols = item.b_rows - col_base;          // valid columns in this half (may be <= 0)
-        const float* xn = xnorm + item.b_row0 + col_base;
-#pragma unroll 1
-        for (int c = 0; c < BX / 64; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * BX + half * (BX / 2) + c * 32, v);
-          tmem_ld_wait();
-          if (c * 32 < ncols) {
-            float dist[32];
-            if (c * 32 + 32 <= ncols) {
-              // L2: ||x||^2 - 2<q,x> (||q||^2 is added once at the end); IP: -<q,x>.
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!metric_ip) {
-                  // xnorm rows are only 4-byte aligned in general (segment starts are arbitrary).
-                  n4.x = __ldg(xn + c * 32 + g * 4 + 0); n4.y = __ldg(xn + c * 32 + g * 4 + 1);
-                  n4.z = __ldg(xn + c * 32 + g * 4 + 2); n4.w = __ldg(xn + c * 32 + g * 4 + 3);
-                }
-                dist[g * 4 + 0] = metric_ip ? -__uint_as_float(v[g * 4 + 0]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 0]), n4.x);
-                dist[g * 4 + 1] = metric_ip ? -__uint_as_float(v[g * 4 + 1]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 1]), n4.y);
-                dist[g * 4 + 2] = metric_ip ? -__uint_as_float(v[g * 4 + 2]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 2]), n4.z);
-                dist[g * 4 + 3] = metric_ip ? -__uint_as_float(v[g * 4 + 3]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 3]), n4.w);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int col = c * 32 + i;
-                float dv = INFINITY;
-                if (col < ncols) {
-                  const float dot = __uint_as_float(v[i]);
-                  dv = metric_ip ? -dot : fmaf(-2.0f, dot, __ldg(xn + col));
-                }
-                dist[i] = dv;
-              }
-            }
-            if constexpr (K == 1) {
-              // argmin of the 32 candidates by a tree (depth 5) instead of a 32-deep serial chain;
-              // the left operand (lower index) wins ties.
-              int idx[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const bool lt = dist[2 * i + 1] < dist[2 * i];
-                dist[i] = lt ? dist[2 * i + 1] : dist[2 * i];
-                idx[i] = lt ? 2 * i + 1 : 2 * i;
-              }
-#pragma unroll
-              for (int w = 8; w >= 1; w >>= 1) {
-#pragma unroll
-                for (int i = 0; i < w; ++i) {
-                  const bool lt = dist[2 * i + 1] < dist[2 * i];
-                  dist[i] = lt ? dist[2 * i + 1] : dist[2 * i];
-                  idx[i] = lt ? idx[2 * i + 1] : idx[2 * i];
-                }
-              }
-              if (dist[0] < best.d[0]) {
-                best.d[0] = dist[0];
-                best.i[0] = col_base + c * 32 + idx[0];
-              }
-            } else {
-              // Cheap prefilter: skip the chunk when nothing beats the current k-th best.
-              float cmin = dist[0];
-#pragma unroll
-              for (int i = 1; i < 32; ++i) cmin = fminf(cmin, dist[i]);
-              if (cmin < best.d[K - 1]) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) best.push(dist[i], col_base + c * 32 + i);
-              }
-            }
-          }
-        }
+        scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
+                          xnorm + item.b_row0 + col_base, col_base, metric_ip, best);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      // Merge the two column halves (their index ranges interleave tile by tile -> lexicographic).
-      if (half == 1) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-          merge_d[j * BQ + r] = best.d[j];
-          merge_i[j * BQ + r] = best.i[j];
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) best.push_lex(merge_d[j * BQ + r], merge_i[j * BQ + r]);
-        if (r < item.q_rows) {
-          const long row = static_cast<long>(item.out_row0) + r;
-          const float qn = metric_ip ? 0.f : qnorm[static_cast<long>(item.q_row0) + r];
-#pragma unroll
-          for (int j = 0; j < K; ++j) {
-            if (j < k_out) {
-              float dv;
-              if (metric_ip) dv = -best.d[j];                 // similarity, descending
-              else dv = fmaxf(best.d[j] + qn, 0.f);           // faiss clamps negative distances to 0
-              if (best.i[j] < 0) dv = metric_ip ? -INFINITY : INFINITY;  // fewer than k bank rows
-              out_d[row * k_out + j] = dv;
-              out_i[row * k_out + j] = best.i[j];
-            }
-          }
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // merge buffer reusable
+      merge_halves_and_store<K>(best, half, r, item.q_rows, static_cast<long>(item.out_row0) + r,
+                                (metric_ip || r >= item.q_rows) ? 0.f : qnorm[static_cast<long>(item.q_row0) + r],
+                                metric_ip, k_out, merge_buf, out_d, out_i);
     }
   }
 
@@ -317,10 +340,238 @@ int launch_knn(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* it
     FP_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kKnnSmem));
   }
-  const int grid = num_items < kNumSMs ? num_items : kNumSMs;
+  const int grid = num_items < num_sms() ? num_items : num_sms();
   ProfScope prof(PROF_KNN, stream, 0.0);
   knn_kernel<K><<<grid, kKnnThreads, kKnnSmem, stream>>>(tmQ, tmX, items, num_items, dim, qnorm,
                                                         xnorm, metric_ip, k_out, out_d, out_i);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+
+// ----------------------------------------------------------------------------------------
+// Pair kernel (tcgen05 cta_group::2) for the tensor-bound regime: many queries against a large bank
+// (K4 of BASELINE configs 3 and 5: 900 queries per crop x the whole bank).
+//
+// The 1-CTA kernel above re-streams the query block with every bank tile and reads both operands of a
+// 128 x 256 x 16 MMA from its own shared memory: 96 B/clk of operand reads + 96 B/clk of TMA writes
+// against a 128 B/clk port - it tops out near 1000 TFLOP/s.  Here a cluster of two CTAs computes a
+// 256-query x 256-bank-row tile per MMA (M256 N256 K16): each CTA keeps ITS 128 query rows RESIDENT
+// in shared memory for the whole bank sweep (d <= 576; wider descriptors stream Q like the GEMM
+// does) and stages only HALF of each bank tile, so per SM the port sees 64 B/clk of operand reads +
+// 32 B/clk of TMA writes.  Work item = up to 256 query rows x one bank segment; epilogue as above
+// (each CTA scans its own 128 x 256 accumulator out of its own TMEM).
+// ----------------------------------------------------------------------------------------
+constexpr int kPairMaxStages = 8;
+constexpr uint32_t kPairHalfX = 128 * BKK * 2;     // this CTA's half of a bank tile k-block: 16 KB
+constexpr uint32_t kPairQBlock = BQ * BKK * 2;     // one k-block of this CTA's 128 query rows: 16 KB
+constexpr uint32_t kPairSmemBudget = 232448 - 1024 /*align*/ - kMergeBytes - 512 /*barriers*/;
+
+struct PairLayout {
+  int q_resident;        // 1: queries stay in smem for the whole item; 0: streamed with the bank
+  int stages;
+  uint32_t q_bytes;      // resident query region
+  uint32_t stage_bytes;  // 16 KB (resident) or 32 KB (streaming: [X half][Q block])
+  uint32_t smem_bytes;   // dynamic shared memory to request
+};
+
+inline PairLayout pair_layout(int dim) {
+  PairLayout L;
+  const uint32_t qb = static_cast<uint32_t>(dim / BKK) * kPairQBlock;
+  const int st_res = qb < kPairSmemBudget ? static_cast<int>((kPairSmemBudget - qb) / kPairHalfX) : 0;
+  if (st_res >= 4) {
+    L.q_resident = 1;
+    L.stages = st_res > kPairMaxStages ? kPairMaxStages : st_res;
+    L.q_bytes = qb;
+    L.stage_bytes = kPairHalfX;
+  } else {
+    L.q_resident = 0;
+    L.stages = static_cast<int>(kPairSmemBudget / (kPairHalfX + kPairQBlock));
+    if (L.stages > kPairMaxStages) L.stages = kPairMaxStages;
+    L.q_bytes = 0;
+    L.stage_bytes = kPairHalfX + kPairQBlock;
+  }
+  L.smem_bytes = L.q_bytes + L.stages * L.stage_bytes + kMergeBytes + 512 + 1024;
+  return L;
+}
+
+template <int K>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kKnnThreads, 1)
+knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
+                const KnnItem* __restrict__ items, int num_items, int dim,
+                const float* __restrict__ qnorm, const float* __restrict__ xnorm, int metric_ip,
+                int k_out, float* __restrict__ out_d, int64_t* __restrict__ out_i, const PairLayout L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* qbuf = smem;
+  uint8_t* stages = smem + L.q_bytes;
+  uint8_t* merge_buf = stages + L.stages * L.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(merge_buf + kMergeBytes);
+  uint64_t* empty_bar = full_bar + kPairMaxStages;
+  uint64_t* tfull_bar = empty_bar + kPairMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* qfull_bar = tempty_bar + 2;
+  uint64_t* qempty_bar = qfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // 0 = leader (issues the MMAs)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < L.stages; ++s) {
+      mbar_init(&full_bar[s], 1);      // leader: one arrive.expect_tx for both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);     // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);     // multicast tcgen05.commit
+      mbar_init(&tempty_bar[a], 16);   // leader: epilogue warps of both CTAs
+    }
+    mbar_init(qfull_bar, 1);
+    mbar_init(qempty_bar, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 2 * BX);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = dim / BKK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int row_off = static_cast<int>(rank) * BQ;   // this CTA's share of the item's query rows / tile's bank rows
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, qphase = 0;
+      for (int it = cluster_id; it < num_items; it += num_clusters) {
+        const KnnItem item = items[it];
+        if (item.q_rows <= 0 || item.b_rows <= 0) continue;
+        if (L.q_resident) {
+          mbar_wait(qempty_bar, qphase ^ 1);   // the previous item's MMAs have all retired
+          if (rank == 0) mbar_arrive_expect_tx(qfull_bar, 2u * L.q_bytes);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_2d_2sm(qbuf + kb * kPairQBlock, &tmQ, qfull_bar, kb * BKK, item.q_row0 + row_off);
+          qphase ^= 1;
+        }
+        const int num_tiles = (item.b_rows + BX - 1) / BX;
+        for (int t = 0; t < num_tiles; ++t) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sx = stages + stage * L.stage_bytes;
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * L.stage_bytes);
+            tma_load_2d_2sm(sx, &tmX, &full_bar[stage], kb * BKK, item.b_row0 + t * BX + row_off);
+            if (!L.q_resident)
+              tma_load_2d_2sm(sx + kPairHalfX, &tmQ, &full_bar[stage], kb * BKK, item.q_row0 + row_off);
+            if (++stage == L.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BQ, BX);
+      int stage = 0;
+      uint32_t phase = 0, qphase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int it = cluster_id; it < num_items; it += num_clusters) {
+        const KnnItem item = items[it];
+        if (item.q_rows <= 0 || item.b_rows <= 0) continue;
+        if (L.q_resident) {
+          mbar_wait(qfull_bar, qphase);
+          qphase ^= 1;
+        }
+        const int num_tiles = (item.b_rows + BX - 1) / BX;
+        for (int t = 0; t < num_tiles; ++t) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + acc * BX;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t sx = smem_u32(stages + stage * L.stage_bytes);
+            const uint64_t bdesc = make_smem_desc_sw128(sx);
+            const uint64_t adesc = make_smem_desc_sw128(L.q_resident ? smem_u32(qbuf) + kb * kPairQBlock
+                                                                     : sx + kPairHalfX);
+#pragma unroll
+            for (int k = 0; k < BKK / 16; ++k)
+              umma_f16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_2sm(&empty_bar[stage]);
+            if (++stage == L.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_2sm(&tfull_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        if (L.q_resident) umma_commit_2sm(qempty_bar);   // both CTAs' query regions are free again
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int sub = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int r = sub * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = cluster_id; it < num_items; it += num_clusters) {
+      const KnnItem item = items[it];
+      if (item.q_rows <= 0 || item.b_rows <= 0) continue;
+      const int num_tiles = (item.b_rows + BX - 1) / BX;
+      const int my_rows = item.q_rows - row_off;   // valid query rows of this CTA (may be <= 0)
+      TopK<K> best;
+      best.init();
+      for (int t = 0; t < num_tiles; ++t) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after_sync();
+        const int col_base = t * BX + half * (BX / 2);
+        scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
+                          xnorm + item.b_row0 + col_base, col_base, metric_ip, best);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      merge_halves_and_store<K>(best, half, r, my_rows, static_cast<long>(item.out_row0) + row_off + r,
+                                (metric_ip || r >= my_rows) ? 0.f
+                                                            : qnorm[static_cast<long>(item.q_row0) + row_off + r],
+                                metric_ip, k_out, merge_buf, out_d, out_i);
+    }
+  }
+
+  // Neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers.
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm(tmem_base, 2 * BX);
+  }
+}
+
+template <int K>
+int launch_knn_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* items, int num_items,
+                    int dim, const float* qnorm, const float* xnorm, int metric_ip, int k_out,
+                    float* out_d, int64_t* out_i, cudaStream_t stream) {
+  const PairLayout L = pair_layout(dim);
+  static bool configured[64] = {};
+  if (per_device_once(configured)) {
+    FP_CUDA_CHECK(cudaFuncSetAttribute(knn_pair_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       232448));
+  }
+  const int max_clusters = num_sms() / 2;
+  const int clusters = num_items < max_clusters ? num_items : max_clusters;
+  ProfScope prof(PROF_KNN_PAIR, stream, 0.0);
+  knn_pair_kernel<K><<<2 * clusters, kKnnThreads, L.smem_bytes, stream>>>(
+      tmQ, tmX, items, num_items, dim, qnorm, xnorm, metric_ip, k_out, out_d, out_i, L);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -467,7 +718,7 @@ int row_sqnorm_f16(const __half* x, float* out, long rows, int dim, cudaStream_t
   if (rows == 0) return 0;
   FP_REQUIRE(dim % 2 == 0, "row_sqnorm: dim must be even");
   long blocks = (rows + 7) / 8;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   ProfScope prof(PROF_FEATURE, stream, static_cast<double>(rows) * dim * 2);
   row_sqnorm_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, out, rows, dim);
   FP_CUDA_CHECK(cudaGetLastError());
@@ -478,7 +729,7 @@ int convert_rows_f16(const float* x, __half* y, long rows, int dim, int l2_norma
                      cudaStream_t stream) {
   if (rows == 0) return 0;
   long blocks = (rows + 7) / 8;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   ProfScope prof(PROF_FEATURE, stream, static_cast<double>(rows) * dim * 6);
   convert_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, rows, dim, l2_normalize);
   FP_CUDA_CHECK(cudaGetLastError());
@@ -501,6 +752,28 @@ int knn_search_items(const __half* q, long q_rows_total, const __half* x, long x
   if (k == 1) FP_KNN_CASE(1);
   if (k == 2) FP_KNN_CASE(2);
   if (k == 3) FP_KNN_CASE(3);
+  if (k <= 5) FP_KNN_CASE(5);
+  if (k <= 8) FP_KNN_CASE(8);
+  FP_KNN_CASE(16);
+#undef FP_KNN_CASE
+}
+
+
+int knn_search_pair_items(const __half* q, long q_rows_total, const __half* x, long x_rows_total, int dim,
+                          const KnnItem* items, int num_items, const float* qnorm, const float* xnorm,
+                          int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream) {
+  FP_REQUIRE(k >= 1 && k <= 16, "knn: k=%d is outside the supported range [1,16]", k);
+  FP_REQUIRE(dim % BKK == 0 && dim >= BKK, "knn: dim=%d must be a positive multiple of %d", dim, BKK);
+  if (num_items <= 0 || q_rows_total <= 0) return 0;
+  FP_REQUIRE(x_rows_total > 0, "knn: the index is empty");
+  CUtensorMap tmQ, tmX;
+  if (make_tma_2d_f16(&tmQ, q, q_rows_total, dim, dim, BQ) != 0) return 3;
+  if (make_tma_2d_f16(&tmX, x, x_rows_total, dim, dim, 128) != 0) return 3;
+#define FP_KNN_CASE(KK)                                                                               \
+  return launch_knn_pair<KK>(tmQ, tmX, items, num_items, dim, qnorm, xnorm, metric_ip, k, out_d, out_i, \
+                             stream)
+  if (k == 1) FP_KNN_CASE(1);
+  if (k <= 3) FP_KNN_CASE(3);
   if (k <= 5) FP_KNN_CASE(5);
   if (k <= 8) FP_KNN_CASE(8);
   FP_KNN_CASE(16);

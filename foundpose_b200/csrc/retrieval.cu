@@ -339,8 +339,11 @@ cyclic_buddies_kernel(const float* __restrict__ points, const int* __restrict__ 
   const int n = q_count[b];
   const long t = top_ids[pair];
   const int kk = min(top_k, n);
-  if (threadIdx.x == 0) out_count[pair] = (t >= 0) ? kk : 0;
-  if (n <= 0 || t < 0) return;
+  // A retrieved template without bank rows (all-zero descriptor, cosine 0: it can enter the top-N when the other
+  // scores are 0 too) has no 1-NN results - the k-NN kernel skips its items - so it yields no correspondences.
+  const bool usable = t >= 0 && tpl_off[t + 1] > tpl_off[t];
+  if (threadIdx.x == 0) out_count[pair] = usable ? kk : 0;
+  if (n <= 0 || !usable) return;
   const int qs = q_start[b];
   const int ts = tpl_off[t];
   const int64_t* q2o_p = q2o + static_cast<long>(pair) * max_q;
@@ -414,7 +417,7 @@ int tfidf_histogram(const int64_t* word_ids, const float* word_dists, int k, con
 int row_norm_f32(const float* x, float* out, int rows, int dim, cudaStream_t stream) {
   if (rows <= 0) return 0;
   int blocks = (rows + 7) / 8;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(rows) * dim * 4);
   row_norm_f32_kernel<<<blocks, 256, 0, stream>>>(x, out, rows, dim);
   FP_CUDA_CHECK(cudaGetLastError());

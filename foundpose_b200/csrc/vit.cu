@@ -169,7 +169,7 @@ int fp_vit_forward(fp_vit* handle, const float* images, int batch, int layer, in
       }
       const int which = facet - 1;  // 1 = query, 2 = key, 3 = value
       fp::ProfScope prof(fp::PROF_VIT_MISC, stream, static_cast<double>(M) * D * 6);
-      fp::facet_gather_kernel<<<fp::kNumSMs * 4, 256, 0, stream>>>(h->qkv, h->facet_x, M, D, heads, which);
+      fp::facet_gather_kernel<<<fp::num_sms() * 4, 256, 0, stream>>>(h->qkv, h->facet_x, M, D, heads, which);
       FP_CUDA_CHECK(cudaGetLastError());
       final_src = h->facet_x;
       break;

@@ -181,7 +181,7 @@ final_norm_tokens_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
-inline int grid_for(long work_items, int per_block, int max_blocks = kNumSMs * 8) {
+inline int grid_for(long work_items, int per_block, int max_blocks = num_sms() * 8) {
   long g = (work_items + per_block - 1) / per_block;
   if (g < 1) g = 1;
   return static_cast<int>(g > max_blocks ? max_blocks : g);

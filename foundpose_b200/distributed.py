@@ -56,6 +56,9 @@ def broadcast_object_repre(repre: Any, src: int = 0, device: Optional[torch.devi
         return repre
     from foundpose_b200.utils import projector_util, repre_util
 
+    if device is None and dist.get_backend() == "nccl":
+        # An NCCL-only group cannot broadcast CPU tensors: stage them on this rank's GPU.
+        device = torch.device("cuda", torch.cuda.current_device())
     rank = dist.get_rank()
     is_src = rank == src
     fields = [f.name for f in dataclasses.fields(repre_util.FeatureBasedObjectRepre)]

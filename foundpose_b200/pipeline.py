@@ -25,7 +25,12 @@ import torch
 from foundpose_b200 import _native
 
 
-def _pad_cols(x: torch.Tensor, mult: int = 64) -> torch.Tensor:
+# Descriptor rows are padded to a multiple of 128 columns everywhere: the PCA GEMM writes N % 128 == 0 columns
+# (PCAProjector.device_state) and the bank rows it is matched against must have the same width.
+DESC_PAD = 128
+
+
+def _pad_cols(x: torch.Tensor, mult: int = DESC_PAD) -> torch.Tensor:
     d = x.shape[1]
     dp = (d + mult - 1) // mult * mult
     if dp == d:
@@ -39,7 +44,10 @@ class ObjectIndex:
     def __init__(self, repre: Any, device: torch.device, num_templates: Optional[int] = None) -> None:
         dev = torch.device(device)
         self.device = dev
-        feat = repre.feat_vectors.to(dev, torch.float32)
+        # fp16 rows (a bank that was packed before, e.g. received through broadcast_object_repre) are taken as they
+        # are; fp32 rows (repre.pth, utils/repre_util.py:143-210) are converted once.
+        packed16 = repre.feat_vectors.dtype == torch.float16
+        feat = repre.feat_vectors.to(dev) if packed16 else repre.feat_vectors.to(dev, torch.float32)
         tpl_ids = repre.feat_to_template_ids.to(dev).to(torch.int64)
         self.feat_dim = feat.shape[1]
         # Bank rows must be contiguous per template. gen_repre builds them that way
@@ -62,7 +70,7 @@ class ObjectIndex:
         off[1:] = torch.cumsum(counts, 0)
         self.tpl_off = off.to(torch.int32).contiguous()
         self.max_template_rows = int(counts.max().item()) if num_templates else 0
-        self.bank16 = _native.convert_rows_f16(_pad_cols(feat))
+        self.bank16 = _pad_cols(feat) if packed16 else _native.convert_rows_f16(_pad_cols(feat))
         self.bank_sqnorm = _native.row_sqnorm_f16(self.bank16)
         self.dim_padded = self.bank16.shape[1]
         self.vertices = repre.vertices.to(dev, torch.float32).contiguous() if repre.vertices is not None else None
@@ -256,17 +264,26 @@ class CropBatchPipeline:
         self.engine = RetrievalEngine(index, batch, self.stride, top_n_templates, top_k_buddies)
 
     @torch.no_grad()
-    def run(self, images: torch.Tensor, masks_u8: torch.Tensor) -> MatchOutputs:
-        """images fp32 [B,3,H,W] in [0,1], masks uint8 [B,H,W]; both on the pipeline's device."""
+    def run(self, images: torch.Tensor, masks_u8: torch.Tensor, desc_out: Optional[torch.Tensor] = None
+            ) -> MatchOutputs:
+        """images fp32 [B,3,H,W] in [0,1], masks uint8 [B,H,W]; both on the pipeline's device.
+
+        desc_out (optional, fp16 [B*stride, dim_padded]): where the projected query descriptors are written (and
+        matched from) instead of the pipeline's own buffer - e.g. a slice of a larger query set that is searched
+        against the whole bank afterwards."""
         assert images.shape[0] == self.batch and masks_u8.shape[0] == self.batch
+        desc = self.proj16 if desc_out is None else desc_out
+        assert desc.shape == self.proj16.shape and desc.dtype == torch.float16 and desc.is_contiguous()
         self.extractor.forward_tokens(images, want_f16=False, want_cls=False, out_tokens=self.tokens)
         _native.filter_points_by_mask(self.grid_points, masks_u8, self.q_points, self.q_ids, self.q_count)
         _native.sample_features(self.tokens, self.hp, self.wp, self.q_points, self.q_count,
                                 float(self.crop_w), float(self.crop_h), None, self.sampled16)
         if self.projector is not None:
             _native.pca_project(self.sampled16, self.projector["components16"], self.projector["bias"],
-                                self.proj32, self.proj16)
-        return self.engine.match(self.proj16, self.q_points, self.q_count)
+                                self.proj32, desc)
+        elif desc_out is not None:
+            desc.copy_(self.sampled16)
+        return self.engine.match(desc, self.q_points, self.q_count)
 
 
 def outputs_to_corresp_list(out: MatchOutputs, crop: int, debug: bool = False) -> List[Dict[str, torch.Tensor]]:

@@ -221,7 +221,7 @@ def infer(opts: InferOpts, repre_dir: Optional[str] = None, crops_path: Optional
     else:
         t, p, d, w = synthetic_bank
         repre = make_synthetic_repre(extractor.arch.embed_dim, d, t, p, w, device) if rank == 0 else None
-    repre = distributed.broadcast_object_repre(repre, src=0, device=None)
+    repre = distributed.broadcast_object_repre(repre, src=0, device=device)
 
     if crops_path is not None:
         blob = torch.load(crops_path, map_location="cpu")

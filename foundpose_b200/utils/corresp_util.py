@@ -9,6 +9,8 @@ from foundpose_b200.utils import knn_util, logging, misc, repre_util, template_u
 
 logger: logging.Logger = logging.get_logger()
 
+_MAX_ENGINES = 8   # RetrievalEngine instances cached per ObjectIndex (one per 128-row bucket of query counts)
+
 
 def convert_px_indices_to_im_coords(px_indices: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     """Pixel index (i, j) -> image coordinates (i + 0.5, j + 0.5), optionally scaled."""
@@ -79,18 +81,25 @@ def establish_correspondences(query_points: torch.Tensor, query_features: torch.
     if n == 0:
         return []
     knn_k = visual_words_knn_index.k if visual_words_knn_index is not None else None
-    key = (n, top_n_templates, top_k_buddies, knn_k)
+    # One engine (device buffers sized for `stride` query rows) serves every crop whose point count falls in the
+    # same 128-row bucket; the actual count goes in as q_count.  At most _MAX_ENGINES stay cached per object.
+    stride = (n + 127) // 128 * 128
+    key = (stride, top_n_templates, top_k_buddies, knn_k)
     engines = index.__dict__.setdefault("_engines", {})
-    if key not in engines:
-        engines[key] = pipeline.RetrievalEngine(index, 1, n, top_n_templates, top_k_buddies, knn_k)
-    engine = engines[key]
-    feat = query_features.to(torch.float32)
-    if feat.shape[1] != index.dim_padded:
-        feat = torch.nn.functional.pad(feat, (0, index.dim_padded - feat.shape[1]))
-    feat16 = _native.convert_rows_f16(feat.contiguous())
-    pts = query_points.to(dev, torch.float32).contiguous().reshape(1, n, 2)
+    engine = engines.pop(key, None)
+    if engine is None:
+        engine = pipeline.RetrievalEngine(index, 1, stride, top_n_templates, top_k_buddies, knn_k)
+        engine.stage_feat = torch.zeros((stride, index.dim_padded), dtype=torch.float32, device=dev)
+        engine.stage_pts = torch.zeros((1, stride, 2), dtype=torch.float32, device=dev)
+        engine.stage_feat16 = torch.zeros((stride, index.dim_padded), dtype=torch.float16, device=dev)
+    engines[key] = engine                                   # most recently used last
+    while len(engines) > _MAX_ENGINES:
+        engines.pop(next(iter(engines)))
+    engine.stage_feat[:n, : query_features.shape[1]] = query_features.to(torch.float32)
+    engine.stage_pts[0, :n] = query_points.to(dev, torch.float32)
+    _native.convert_rows_f16(engine.stage_feat, out=engine.stage_feat16)
     count = torch.full((1,), n, dtype=torch.int32, device=dev)
-    out = engine.match(feat16, pts, count)
+    out = engine.match(engine.stage_feat16, engine.stage_pts, count)
     corresps = pipeline.outputs_to_corresp_list(out, 0, debug=debug)
     # The engine's buffers are reused by the next call: hand out copies.
     corresps = [{k: v.clone() for k, v in c.items()} for c in corresps]

@@ -19,8 +19,49 @@ from foundpose_b200 import _native
 _MAX_K = 16
 _SPLIT_BELOW_ITEMS = 74     # fewer query blocks than half the SMs -> split the bank
 _SPLIT_MIN_ROWS = 16384
-_NUM_SMS = 148
+_PAIR_ROWS = 256            # query rows per item of the pair kernel (fp_knn_search_pair_items)
+_PAIR_MIN_BANK_ROWS = 8192  # below this the per-item pipeline fill dominates: keep the 1-CTA kernel
+_sm_count = [0]
+
+
+def _num_sms() -> int:
+    """SM count of the current device, read once through the library (cudaDevAttrMultiProcessorCount)."""
+    if _sm_count[0] == 0:
+        _sm_count[0] = _native.num_sms() if torch.cuda.is_available() else 148
+    return _sm_count[0]
 _TARGET_ITEMS = int(os.environ.get("FOUNDPOSE_KNN_TARGET_ITEMS", "592"))   # upper bound on items of a split search
+
+
+def plan_pair_items(nq: int, nb: int, num_clusters: int) -> Tuple[list, list, int, int]:
+    """Work items of a tensor-bound search (nq queries x nb bank rows) for the pair kernel.
+
+    One item = 256 query rows sweeping a bank segment on one CTA pair.  Items that fill whole waves of the
+    `num_clusters` persistent clusters sweep the whole bank and write final results; the remaining `rem` items of the
+    last, partial wave are split into `chunks = num_clusters // rem` bank slices each, so that the tail wave is
+    `1 / chunks` as long and every cluster has work in it.  Their partial top-k lists are merged by fp_knn_merge.
+
+    Returns (direct_items, split_items, chunks, chunk_rows): item tuples (q_row0, q_rows, b_row0, b_rows, out_row0);
+    split items write to a partial buffer laid out [chunks, rem * 256, k] (out_row0 relative to it).
+    """
+    n_pairs = (nq + _PAIR_ROWS - 1) // _PAIR_ROWS
+    full = (n_pairs // num_clusters) * num_clusters
+    rem = n_pairs - full
+    chunks = num_clusters // rem if rem > 0 else 1
+    chunk_rows = 0
+    if chunks >= 2:
+        chunk_rows = ((nb + chunks - 1) // chunks + 255) // 256 * 256
+        chunks = (nb + chunk_rows - 1) // chunk_rows
+    if chunks < 2:
+        full, rem, chunks = n_pairs, 0, 1
+    direct = [(i * _PAIR_ROWS, min(_PAIR_ROWS, nq - i * _PAIR_ROWS), 0, nb, i * _PAIR_ROWS) for i in range(full)]
+    split = []
+    q_pad = rem * _PAIR_ROWS
+    for c in range(chunks if rem else 0):
+        for j in range(rem):
+            q0 = (full + j) * _PAIR_ROWS
+            split.append((q0, min(_PAIR_ROWS, nq - q0), c * chunk_rows, max(0, min(chunk_rows, nb - c * chunk_rows)),
+                          c * q_pad + j * _PAIR_ROWS))
+    return direct, split, chunks, chunk_rows
 
 
 def _choose_num_chunks(n_q: int) -> int:
@@ -29,7 +70,7 @@ def _choose_num_chunks(n_q: int) -> int:
     SM reached 57-88% of the HBM peak on 0.8-7.9 GB banks where four reached 45-75%)."""
     effs = []
     for c in range(1, max(1, _TARGET_ITEMS // n_q) + 1):
-        waves = n_q * c / _NUM_SMS
+        waves = n_q * c / _num_sms()
         effs.append(waves / math.ceil(waves))
     best = max(effs)
     return 1 + next(i for i, e in enumerate(effs) if e >= best - 0.03)
@@ -39,9 +80,11 @@ def _device_for(t: torch.Tensor) -> torch.device:
     return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
 
-def _pad64(x: torch.Tensor) -> torch.Tensor:
+def _pad64(x: torch.Tensor, width: Optional[int] = None) -> torch.Tensor:
     d = x.shape[1]
-    dp = (d + 63) // 64 * 64
+    dp = (d + 63) // 64 * 64 if width is None else width
+    if dp < d:
+        raise ValueError(f"query dimension {d} exceeds the index dimension {dp}")
     x = x.to(torch.float32)
     if dp != d:
         x = torch.nn.functional.pad(x, (0, dp - d))
@@ -93,7 +136,7 @@ class KNN:
             raise NotImplementedError(f"k={self.k} > {_MAX_K} is not supported by the B200 k-NN kernel")
         out_device = data.device
         dev = self._bank16.device
-        q = _pad64(data.detach().to(dev))
+        q = _pad64(data.detach().to(dev), self._bank16.shape[1])   # the index may hold wider, zero-padded rows
         nq = q.shape[0]
         dist = torch.empty((nq, self.k), dtype=torch.float32, device=dev)
         idx = torch.empty((nq, self.k), dtype=torch.int64, device=dev)
@@ -101,15 +144,32 @@ class KNN:
             cosine = self.metric == "cosine"
             q16 = _native.convert_rows_f16(q, l2_normalize=cosine)
             qn = _native.row_sqnorm_f16(q16)
-            n_q = _native.knn_num_items(nq)
-            nb = self._bank16.shape[0]
-            metric = 1 if cosine else 0
-            # Few query blocks against a large bank: split the bank so that all SMs stream it.
-            num_chunks = 1
-            if n_q < _SPLIT_BELOW_ITEMS and nb >= _SPLIT_MIN_ROWS:
-                want = _choose_num_chunks(n_q)
-                chunk_rows = max(256, ((nb + want - 1) // want + 255) // 256 * 256)
-                num_chunks = (nb + chunk_rows - 1) // chunk_rows
+            dist, idx = self.search_packed(q16, qn, dist, idx)
+            if cosine:
+                dist = 1.0 - dist  # cosine similarity -> cosine distance (reference :98)
+        return dist.to(out_device), idx.to(out_device)
+
+    def search_packed(self, q16: torch.Tensor, qn: torch.Tensor, dist: Optional[torch.Tensor] = None,
+                      idx: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Search with already packed fp16 query rows (and their fp32 ||q||^2): no conversion, no host sync.
+
+        Returns raw kernel outputs (squared L2 ascending, or inner products descending for metric "cosine").
+        Picks the pass structure from the problem shape: the pair kernel when the search is tensor-bound (>= 74
+        query blocks x a large bank), bank slices over all SMs when it is HBM-bound (few query blocks x a large
+        bank), one item per query block otherwise."""
+        dev = q16.device
+        nq, nb = q16.shape[0], self._bank16.shape[0]
+        metric = 1 if self.metric == "cosine" else 0
+        if dist is None:
+            dist = torch.empty((nq, self.k), dtype=torch.float32, device=dev)
+            idx = torch.empty((nq, self.k), dtype=torch.int64, device=dev)
+        n_q = _native.knn_num_items(nq)
+        if n_q >= _num_sms() // 2 and nb >= _PAIR_MIN_BANK_ROWS:
+            return self._search_pairs(q16, qn, metric, dist, idx)
+        if n_q < _SPLIT_BELOW_ITEMS and nb >= _SPLIT_MIN_ROWS:
+            want = _choose_num_chunks(n_q)
+            chunk_rows = max(256, ((nb + want - 1) // want + 255) // 256 * 256)
+            num_chunks = (nb + chunk_rows - 1) // chunk_rows
             if num_chunks > 1:
                 q_pad = n_q * 128
                 items = _native.new_knn_items(n_q * num_chunks, dev)
@@ -118,15 +178,43 @@ class KNN:
                 part_i = torch.full((num_chunks * q_pad, self.k), -1, dtype=torch.int64, device=dev)
                 _native.knn_search_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_q * num_chunks,
                                          metric, self.k, part_d, part_i)
-                _native.knn_merge(part_d, part_i, num_chunks, q_pad, nq, self.k, chunk_rows, nb, cosine, dist, idx)
-            else:
-                items = _native.new_knn_items(n_q, dev)
-                _native.knn_items_dense(items, nq, 0, nb)
-                _native.knn_search_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_q, metric, self.k,
-                                         dist, idx)
-            if cosine:
-                dist = 1.0 - dist  # cosine similarity -> cosine distance (reference :98)
-        return dist.to(out_device), idx.to(out_device)
+                _native.knn_merge(part_d, part_i, num_chunks, q_pad, nq, self.k, chunk_rows, nb, metric == 1,
+                                  dist, idx)
+                return dist, idx
+        items = _native.new_knn_items(n_q, dev)
+        _native.knn_items_dense(items, nq, 0, nb)
+        _native.knn_search_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_q, metric, self.k, dist, idx)
+        return dist, idx
+
+    def _search_pairs(self, q16: torch.Tensor, qn: torch.Tensor, metric: int, dist: torch.Tensor,
+                      idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Tensor-bound regime: ONE launch of the pair kernel over whole-wave items (final results) and the split
+        items of the tail wave (partial lists behind the final rows of the same buffers), then the tail merge."""
+        dev = q16.device
+        nq, nb = q16.shape[0], self._bank16.shape[0]
+        key = (nq, nb, self.k, str(dev))
+        plan = getattr(self, "_pair_plan", None)
+        if plan is None or plan[0] != key:
+            direct, split, chunks, chunk_rows = plan_pair_items(nq, nb, _num_sms() // 2)
+            split = [(q0, qr, b0, br, o0 + nq) for (q0, qr, b0, br, o0) in split]   # partials live behind row nq
+            rem = len(split) // chunks if split else 0
+            rows = nq + chunks * rem * _PAIR_ROWS if split else nq
+            plan = (key, _native.knn_items_from_host(direct + split, dev), len(direct), len(split), chunks, chunk_rows,
+                    torch.empty((rows, self.k), dtype=torch.float32, device=dev),
+                    torch.empty((rows, self.k), dtype=torch.int64, device=dev))
+            self._pair_plan = plan
+        _, items, n_direct, n_split, chunks, chunk_rows, buf_d, buf_i = plan
+        if n_split == 0:
+            _native.knn_search_pair_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_direct, metric, self.k,
+                                          dist, idx)
+            return dist, idx
+        _native.knn_search_pair_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_direct + n_split, metric,
+                                      self.k, buf_d, buf_i)
+        q_pad = (n_split // chunks) * _PAIR_ROWS
+        first_tail = n_direct * _PAIR_ROWS
+        _native.knn_merge(buf_d[nq:], buf_i[nq:], chunks, q_pad, nq - first_tail, self.k, chunk_rows, nb, metric == 1,
+                          buf_d[first_tail:], buf_i[first_tail:])
+        return buf_d[:nq], buf_i[:nq]
 
     def serialize_index(self) -> None:
         pass

@@ -51,8 +51,10 @@ class PCAProjector(Projector):
     def fit(self, data_x: torch.Tensor, data_y: Optional[torch.Tensor] = None, **kwargs: Any) -> None:
         """PCA fit of the offline bank build (reference utils/projector_util.py:53-64, scripts/gen_repre.py:272-284).
 
-        CUDA tensors are fitted on the GPU with the algorithm scikit-learn itself calls "covariance_eigh"
-        (sklearn/decomposition/_pca.py, chosen by `PCA(...)` for tall data): covariance of the centred samples,
+        CUDA tensors are fitted on the GPU with the algorithm scikit-learn calls "covariance_eigh"
+        (sklearn/decomposition/_pca.py; its `svd_solver="auto"` takes it for tall data with few features, but picks the
+        non-deterministic "randomized" solver for 1024-d features with 256 components, so a GPU-built bank is comparable
+        to the reference's only up to the subspace, not bit for bit): covariance of the centred samples,
         symmetric eigendecomposition, eigenvectors flipped so that the largest entry of every component is positive
         (`svd_flip(u_based_decision=False)`).  The covariance - the O(n D^2) part - runs on the tcgen05 GEMM with the
         fp32 samples split into two fp16 terms (x = hi + lo, the lo.lo product is below fp32 resolution); the D x D
@@ -121,8 +123,11 @@ class PCAProjector(Projector):
             d_pad = (d_out + 127) // 128 * 128
             comp_p = torch.zeros(d_pad, d_in)
             comp_p[:d_out] = comp
+            # The GEMM multiplies by the fp16-rounded components, so the folded bias -(mean . C^T) uses the same
+            # rounded values: out = (x - mean) . C16^T exactly as if the mean had been subtracted first.
+            comp16 = comp.to(torch.float16).to(torch.float32)
             bias = torch.zeros(d_pad)
-            bias[:d_out] = torch.from_numpy(-(mean.reshape(1, -1).numpy() @ comp.numpy().T).reshape(-1))
+            bias[:d_out] = torch.from_numpy(-(mean.reshape(1, -1).numpy() @ comp16.numpy().T).reshape(-1))
             self._device_state[key] = {
                 "components16": comp_p.to(device, torch.float16).contiguous(),
                 "bias": bias.to(device).contiguous(),

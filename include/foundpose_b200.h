@@ -165,6 +165,15 @@ int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_
                         const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
                         int dim, const fp_knn_item* items, int num_items, int metric, int k,
                         float* out_d, int64_t* out_i, void* stream);
+/* Same search for the tensor-bound regime (many queries x a large bank: the benchmark search K4 of
+ * BASELINE.json configs 3 and 5, queries of all crops vs the WHOLE bank; utils/knn_util.py:65-106 with
+ * the full feat_vectors as the index).  Items hold up to 256 query rows (q_rows <= 256): a cluster of
+ * two CTAs keeps them resident in shared memory and sweeps the bank segment with cta_group::2 MMAs.
+ * Same outputs, tie rule and indices relative to b_row0 as fp_knn_search_items. */
+int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const float* q_sqnorm,
+                             const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
+                             int dim, const fp_knn_item* items, int num_items, int metric, int k,
+                             float* out_d, int64_t* out_i, void* stream);
 
 /* ---- crop stage in front of the extractor ------------------------- */
 /* warp_image x2 + array_to_tensor + calc_2d_box for B instances (scripts/infer.py:427-456,
@@ -271,8 +280,10 @@ int fp_pnp_ransac(const float* coord_2d, const float* coord_3d, const int32_t* c
 /* ---- launch accounting and per-kernel timing (used by bench.py) ---------------------------- */
 /* Number of kernels this library has launched since it was loaded (all threads). */
 unsigned long long fp_launch_count(void);
+/* Streaming multiprocessors of the current device (persistent grids are sized from it). */
+int fp_num_sms(void);
 /* Same, for one kernel family: 0 gemm, 1 attention, 2 layernorm, 3 vit misc, 4 knn,
- * 5 feature ops, 6 retrieval. */
+ * 5 feature ops, 6 retrieval, 7 full-bank k-NN (pair kernel). */
 unsigned long long fp_launch_count_category(int category);
 /* When on, every launch is bracketed by CUDA events on its stream. */
 int fp_profile_enable(int on);

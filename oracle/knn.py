@@ -6,9 +6,17 @@ conda_foundpose_gpu.yaml:19, absent from /root/reference and from this image):
                      (utils/template_util.py:26 "The distances returned by faiss are squared")
   * metric "cosine": rows L2-normalised at fit and search time, inner product, distance = 1 - sim
                      (utils/knn_util.py:54-60, 93-98)
-faiss's published algorithm for flat indexes with >= 20 queries (exhaustive_L2sqr_blas) is
-d(x, y) = ||x||^2 + ||y||^2 - 2 <x, y> evaluated in fp32 with negatives clamped to 0; we restate
-exactly that.  Ties are broken by ascending index (canonical rule).
+faiss's published algorithm for flat indexes (faiss/utils/distances.cpp, v1.8.0):
+  * nq >= distance_compute_blas_threshold (= 20): exhaustive_L2sqr_blas - queries in blocks of 4096, database in
+    blocks of 1024, d(x, y) = ||x||^2 + ||y||^2 - 2 <x, y> with the inner products from one sgemm per block pair,
+    evaluated in fp32 with negatives clamped to 0, candidates pushed into a per-query heap -> `knn_l2`,
+    `knn_l2_blocked` (same arithmetic, database streamed block by block for banks that do not fit a dense
+    distance matrix);
+  * nq < 20: exhaustive_L2sqr_seq - every distance evaluated directly as sum_i (x_i - y_i)^2 (fvec_L2sqr), no
+    norm expansion, so the low-order bits differ from the blas branch -> `knn_l2_direct`.
+`knn_l2_faiss` dispatches on nq like faiss does.  Ties are broken by ascending index (canonical rule,
+SURVEY.md §8c(i)); faiss's heap order for exact ties is implementation-defined.
+Parity unpinned against faiss binaries (faiss is absent from /root/reference and from this image).
 """
 
 from __future__ import annotations
@@ -56,6 +64,61 @@ def knn_l2(query: torch.Tensor, bank: torch.Tensor, k: int, chunk: int = 4096) -
     if not outs_d:
         return torch.empty(0, k), torch.empty(0, k, dtype=torch.int64)
     return torch.cat(outs_d), torch.cat(outs_i)
+
+
+def knn_l2_direct(query: torch.Tensor, bank: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """faiss exhaustive_L2sqr_seq (nq < 20): d = sum_i (q_i - x_i)^2 accumulated in fp32 (fvec_L2sqr)."""
+    q = query.to(torch.float32)
+    x = bank.to(torch.float32)
+    d = torch.stack([((x - q[i]) ** 2).sum(dim=1) for i in range(q.shape[0])]) if q.shape[0] else \
+        torch.empty(0, x.shape[0])
+    return _topk_smallest(d, k)
+
+
+FAISS_BLAS_THRESHOLD = 20   # faiss::distance_compute_blas_threshold
+
+
+def knn_l2_faiss(query: torch.Tensor, bank: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """IndexFlatL2.search as faiss dispatches it: direct distances below 20 queries, the blas expansion above."""
+    if query.shape[0] < FAISS_BLAS_THRESHOLD:
+        return knn_l2_direct(query, bank, k)
+    return knn_l2(query, bank, k)
+
+
+def merge_topk(d_a: torch.Tensor, i_a: torch.Tensor, d_b: torch.Tensor, i_b: torch.Tensor, k: int
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merges two per-query candidate lists by (distance, index) ascending."""
+    d = torch.cat([d_a, d_b], dim=1)
+    i = torch.cat([i_a, i_b], dim=1)
+    # lexicographic: stable sort by index first, then stable sort by distance
+    o1 = torch.sort(i, dim=1, stable=True).indices
+    d, i = torch.gather(d, 1, o1), torch.gather(i, 1, o1)
+    o2 = torch.sort(d, dim=1, stable=True).indices
+    return torch.gather(d, 1, o2)[:, :k].contiguous(), torch.gather(i, 1, o2)[:, :k].contiguous()
+
+
+def knn_l2_blocked(query: torch.Tensor, bank_blocks, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """exhaustive_L2sqr_blas over a bank delivered block by block.
+
+    `bank_blocks` yields (first_row, rows fp32 [n, d]) in ascending row order; every block contributes its k best
+    (same fp32 expansion as `knn_l2`), merged by (distance, global index) - what faiss's per-query heap holds after
+    the last database block.  Used for the full-bank search K4 of BASELINE configs 3 and 5, where the bank
+    (10.24 M rows) is far larger than a dense distance matrix allows.
+    """
+    best_d = best_i = None
+    for row0, rows in bank_blocks:
+        kk = min(k, rows.shape[0])
+        d, i = knn_l2(query, rows, kk)
+        i = i + int(row0)
+        if best_d is None:
+            best_d, best_i = d, i
+        else:
+            best_d, best_i = merge_topk(best_d, best_i, d, i, k)
+    if best_d is not None and best_d.shape[1] < k:
+        pad = k - best_d.shape[1]
+        best_d = torch.cat([best_d, torch.full((best_d.shape[0], pad), float("inf"))], dim=1)
+        best_i = torch.cat([best_i, torch.full((best_i.shape[0], pad), -1, dtype=torch.int64)], dim=1)
+    return best_d, best_i
 
 
 def knn_cosine(query: torch.Tensor, bank: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:

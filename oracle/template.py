@@ -62,6 +62,39 @@ def calc_tfidf_descriptors(feat_vectors: torch.Tensor, feat_to_word_ids: torch.T
     return torch.stack(descs, dim=0), idfs
 
 
+def calc_tfidf_descriptors_vectorised(feat_vectors: torch.Tensor, feat_to_word_ids: torch.Tensor,
+                                      feat_to_template_ids: torch.Tensor, feat_words: torch.Tensor,
+                                      num_templates: int, tfidf_knn_k: int, chunk: int = 1 << 18
+                                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`calc_tfidf_descriptors` (hard assignment) without the per-template Python loops.
+
+    Same arithmetic as utils/template_util.py:74-123 with tfidf_soft_assign=False - idf_i = log(N / N_i) from
+    the nearest-word assignment, every feature adds (1/sqrt(k)) / n_t * idf to each of its k nearest words of
+    its template's descriptor - expressed as chunked matrix products and one scatter_add, so that the 10 k-template
+    bank of BASELINE configs[2] can be set up in seconds (on whatever device the tensors live on).  Only used to
+    PREPARE benchmark inputs of the reference arm; checked against the loop version in tests/test_oracle_golden.py.
+    """
+    dev = feat_vectors.device
+    num_words = feat_words.shape[0]
+    tpl = feat_to_template_ids.to(torch.int64)
+    pair = torch.unique(tpl * num_words + feat_to_word_ids.to(torch.int64))
+    occ = torch.bincount(pair % num_words, minlength=num_words)
+    idfs = torch.log(torch.as_tensor(float(num_templates), device=dev) / occ.to(torch.float32))
+    counts = torch.bincount(tpl, minlength=num_templates).to(torch.float32)
+    words = feat_words.to(torch.float32)
+    wn = (words * words).sum(dim=1).unsqueeze(0)
+    descs = torch.zeros(num_templates * num_words, dtype=torch.float32, device=dev)
+    w = 1.0 / (tfidf_knn_k ** 0.5)
+    for s in range(0, feat_vectors.shape[0], chunk):
+        x = feat_vectors[s:s + chunk].to(torch.float32)
+        d = (x * x).sum(dim=1, keepdim=True) + wn - 2.0 * (x @ words.t())
+        ids = torch.topk(d, tfidf_knn_k, dim=1, largest=False).indices            # [n, k]
+        t = tpl[s:s + chunk]
+        val = (w / counts[t]).unsqueeze(1) * idfs[ids]
+        descs.scatter_add_(0, (t.unsqueeze(1) * num_words + ids).reshape(-1), val.reshape(-1))
+    return descs.reshape(num_templates, num_words), idfs
+
+
 def tfidf_matching(query_features: torch.Tensor, centroids: torch.Tensor, idfs: torch.Tensor,
                    template_descs: torch.Tensor, top_n_templates: int, knn_k: int = 3,
                    knn_metric: str = "l2", soft_assign: bool = False,

@@ -188,3 +188,33 @@ def test_knn_split_chunk_count_fills_whole_waves():
         waves = n_q * c / 148
         assert 1 <= c <= max(1, 592 // n_q)
         assert waves / math.ceil(waves) >= 0.93, (n_q, c)
+
+
+def test_pair_item_plan_covers_every_query_once_and_fills_the_tail_wave():
+    """Host logic of the tensor-bound k-NN path (fp_knn_search_pair_items): whole waves of 74 CTA pairs sweep the
+    whole bank, the items of the last partial wave are split into bank slices that together cover it exactly."""
+    from foundpose_b200.utils import knn_util
+
+    for nq, nb in [(460800, 10240000), (57600, 10240000), (21541, 9000), (9473, 8193), (256 * 74, 50000), (300, 9000)]:
+        direct, split, chunks, chunk_rows = knn_util.plan_pair_items(nq, nb, 74)
+        assert len(direct) % 74 == 0 or not split     # a tail of more than 37 items cannot be split: left whole
+        covered = sorted((q0, q0 + qr) for q0, qr, b0, br, _ in direct)
+        tail = {}
+        for q0, qr, b0, br, o0 in split:
+            assert 0 < br <= chunk_rows and b0 % 256 == 0 and chunk_rows % 256 == 0
+            tail.setdefault((q0, qr), []).append((b0, br))
+        for (q0, qr), slices in tail.items():
+            slices.sort()
+            assert slices[0][0] == 0 and sum(br for _, br in slices) == nb            # slices tile the bank
+            assert all(a[0] + a[1] == b[0] for a, b in zip(slices, slices[1:]))
+            assert len(slices) == chunks
+            covered.append((q0, q0 + qr))
+        covered.sort()
+        assert covered[0][0] == 0 and covered[-1][1] == nq
+        assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))               # every query exactly once
+        if split:
+            assert len(split) <= 74 and len(split) > 74 // 2                          # the tail wave is (nearly) full
+        # partial results of slice c, tail item j live at rows c * q_pad + j * 256 of the partial buffer
+        q_pad = (len(split) // chunks) * 256 if split else 0
+        assert sorted(o0 for *_, o0 in split) == sorted(c * q_pad + j * 256 for c in range(chunks if split else 0)
+                                                        for j in range(len(split) // chunks))

@@ -69,7 +69,12 @@ def test_pca_vs_golden(gold):
 
 @pytest.mark.parametrize("nq,nb,dim,k", [(150, 32, 64, 3), (1000, 2048, 256, 3), (900, 1024, 384, 1),
                                          (37, 5000, 128, 5), (129, 129, 64, 8), (5, 3, 64, 1),
-                                         (100, 40000, 128, 5), (300, 70001, 64, 1)])   # last two: split-bank path
+                                         (100, 40000, 128, 5), (300, 70001, 64, 1),    # split-bank path
+                                         # pair kernel (cta_group::2, >= 74 query blocks x >= 8192 bank rows):
+                                         (9500, 9000, 384, 5),      # queries resident in smem, one partial wave
+                                         (21541, 9000, 64, 5),      # one whole wave + a split tail wave + merge
+                                         (9600, 8200, 640, 3),      # d > 576: queries streamed with the bank
+                                         (9473, 8193, 128, 1)])     # ragged last item / last tile, k = 1
 def test_knn_l2_vs_oracle(nq, nb, dim, k):
     from foundpose_b200.utils import knn_util
     from oracle import knn as oknn
