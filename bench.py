@@ -670,9 +670,9 @@ def spot_check(pipe, index, host_images, host_masks, sd, arch, layer, pdict, wl,
         n = st1["n_queries"]
         s = pipe.stride
         q = q_desc16[crop * s: crop * s + n].float().cpu()
-        st2 = ocheck.retrieval_stage(index, pipe.engine.out, crop, st1["oracle_points"], q, wl["top_k"])
-        res.update({k: st2[k] for k in ("templates_equal", "template_gap", "pairs", "pairs_sure", "pairs_exact",
-                                        "corr_agree", "template_score_err")})
+        st2 = ocheck.retrieval_stage(index, pipe.engine, crop, st1["oracle_points"], q, wl["top_k"])
+        res.update({k: st2[k] for k in ("templates_equal", "template_gap", "pairs", "pairs_exact", "nn_checked",
+                                        "nn_sure_frac", "nn_equal_frac", "corr_agree", "template_score_err")})
         assert st2["templates_equal"] or not st2["templates_sure"], "template ids differ from the oracle"
         if k4_d is not None:
             nq4 = min(8, n)

@@ -250,6 +250,11 @@ int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const floa
                                    static_cast<cudaStream_t>(stream));
 }
 
+int fp_knn_set_flags(int flags) {
+  fp::knn_set_flags(flags);
+  return 0;
+}
+
 int fp_crop_warp(const void* images, int src_is_f32, int num_images, int src_h, int src_w,
                  int channels, const uint8_t* masks, const double* params, int B, int crop_w,
                  int crop_h, float* out_images, uint8_t* out_masks, float* out_boxes,

@@ -90,6 +90,8 @@ int knn_search_pair_items(const __half* q, long q_rows_total, const __half* x, l
                           int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream);
 
 
+void knn_set_flags(int flags);   // experiment switches of the pair kernel, 0 in production
+
 // ---- crop_warp.cu -----------------------------------------------------------------------
 int crop_warp(const void* images, int src_is_f32, int num_images, int src_h, int src_w, int channels,
               const uint8_t* masks, const double* params, int B, int crop_w, int crop_h,

@@ -33,7 +33,8 @@ constexpr int BX = 256;   // bank rows per tile (128 x 256 x 16 UMMA: 96 B/clk o
 constexpr int BKK = 64;   // K elements per stage
 constexpr int kStages = 4;
 constexpr int kMaxK = 16;
-constexpr uint32_t kMergeBytes = BQ * kMaxK * 8;   // (dist, idx) lists of the second column half
+constexpr uint32_t kXnBytes = 2 * BX * 4;          // ||x||^2 of the current and the next tile
+constexpr uint32_t kMergeBytes = BQ * kMaxK * 8 + kXnBytes;   // (dist, idx) lists of the second column half + xn_s
 constexpr uint32_t kQStage = BQ * BKK * 2;
 constexpr uint32_t kXStage = BX * BKK * 2;
 constexpr uint32_t kStageBytes = kQStage + kXStage;
@@ -76,13 +77,13 @@ struct TopK {
 
 // One epilogue thread's share of a 128 x 256 distance tile: its query row (TMEM lane) x one half (128) of the
 // tile's bank columns, starting at TMEM address `taddr`.  `ncols` = valid columns in this half (may be <= 0),
-// `xn` = ||x||^2 of the half's first column, `col_base` = index of that column relative to the item's segment.
+// `xn` = ||x||^2 of the half's 128 columns STAGED IN SHARED MEMORY by the epilogue warps one tile ahead (a global
+// load per 32-column chunk on the critical path of every tile cost more than the chunk's arithmetic),
+// `col_base` = index of the half's first column relative to the item's segment.
 // L2: ||x||^2 - 2<q,x> (||q||^2 is added once per item); IP: -<q,x>.
 template <int K>
 __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, const float* __restrict__ xn,
                                                int col_base, int metric_ip, TopK<K>& best) {
-  // 16-byte loads of the bank norms when the segment start allows it (always for full-bank searches).
-  const bool xn_vec = (reinterpret_cast<uintptr_t>(xn) & 15) == 0;
 #pragma unroll 1
   for (int c = 0; c < BX / 64; ++c) {
     uint32_t v[32];
@@ -94,14 +95,7 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, const 
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!metric_ip) {
-            if (xn_vec) {
-              n4 = __ldg(reinterpret_cast<const float4*>(xn + c * 32 + g * 4));
-            } else {
-              n4.x = __ldg(xn + c * 32 + g * 4 + 0); n4.y = __ldg(xn + c * 32 + g * 4 + 1);
-              n4.z = __ldg(xn + c * 32 + g * 4 + 2); n4.w = __ldg(xn + c * 32 + g * 4 + 3);
-            }
-          }
+          if (!metric_ip) n4 = *reinterpret_cast<const float4*>(xn + c * 32 + g * 4);
           dist[g * 4 + 0] = metric_ip ? -__uint_as_float(v[g * 4 + 0]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 0]), n4.x);
           dist[g * 4 + 1] = metric_ip ? -__uint_as_float(v[g * 4 + 1]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 1]), n4.y);
           dist[g * 4 + 2] = metric_ip ? -__uint_as_float(v[g * 4 + 2]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 2]), n4.z);
@@ -114,7 +108,7 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, const 
           float dv = INFINITY;
           if (col < ncols) {
             const float dot = __uint_as_float(v[i]);
-            dv = metric_ip ? -dot : fmaf(-2.0f, dot, __ldg(xn + col));
+            dv = metric_ip ? -dot : fmaf(-2.0f, dot, xn[col]);
           }
           dist[i] = dv;
         }
@@ -144,16 +138,29 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, const 
         }
       } else {
         // Cheap prefilter: skip the chunk when nothing beats the current k-th best.
-        float cmin = dist[0];
+        float m[16];   // min as a tree (depth 5), not a 31-deep dependent chain
 #pragma unroll
-        for (int i = 1; i < 32; ++i) cmin = fminf(cmin, dist[i]);
-        if (cmin < best.d[K - 1]) {
+        for (int i = 0; i < 16; ++i) m[i] = fminf(dist[2 * i], dist[2 * i + 1]);
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+          for (int i = 0; i < w; ++i) m[i] = fminf(m[2 * i], m[2 * i + 1]);
+        }
+        if (m[0] < best.d[K - 1]) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) best.push(dist[i], col_base + c * 32 + i);
         }
       }
     }
   }
+}
+
+// ||x||^2 of a tile's 256 bank columns: one column per epilogue thread (et = 0..255), zero past the segment.
+__device__ __forceinline__ float load_tile_xnorm(const float* __restrict__ xnorm, const KnnItem& item, int tile,
+                                                 int num_tiles, int et, int metric_ip) {
+  const int col = tile * BX + et;
+  if (metric_ip || tile >= num_tiles || col >= item.b_rows) return 0.f;
+  return __ldg(xnorm + item.b_row0 + col);
 }
 
 // Merges the two column halves of an item through shared memory (their index ranges interleave tile by tile ->
@@ -203,6 +210,7 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* merge_buf = smem + kStages * kStageBytes;
+  float* xn_s = reinterpret_cast<float*>(merge_buf + BQ * kMaxK * 8);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(merge_buf + kMergeBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
@@ -296,6 +304,7 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const int sub = warp & 3;
     const int half = (warp - 4) >> 2;
     const int r = sub * 32 + lane;
+    const int et = threadIdx.x - 128;          // 0..255: the tile column whose ||x||^2 this thread stages
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -305,17 +314,22 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       const int num_tiles = (item.b_rows + BX - 1) / BX;
       TopK<K> best;
       best.init();
+      xn_s[et] = load_tile_xnorm(xnorm, item, 0, num_tiles, et, metric_ip);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int t = 0; t < num_tiles; ++t) {
+        const float xn_next = load_tile_xnorm(xnorm, item, t + 1, num_tiles, et, metric_ip);   // lands during the scan
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
         scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
-                          xnorm + item.b_row0 + col_base, col_base, metric_ip, best);
+                          xn_s + (t & 1) * BX + half * (BX / 2), col_base, metric_ip, best);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+        xn_s[((t + 1) & 1) * BX + et] = xn_next;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // slot (t+1)&1 complete; slot t&1 no longer read
       }
       merge_halves_and_store<K>(best, half, r, item.q_rows, static_cast<long>(item.out_row0) + r,
                                 (metric_ip || r >= item.q_rows) ? 0.f : qnorm[static_cast<long>(item.q_row0) + r],
@@ -373,6 +387,7 @@ struct PairLayout {
   uint32_t q_bytes;      // resident query region
   uint32_t stage_bytes;  // 16 KB (resident) or 32 KB (streaming: [X half][Q block])
   uint32_t smem_bytes;   // dynamic shared memory to request
+  int flags;             // experiment switches (g_knn_flags)
 };
 
 inline PairLayout pair_layout(int dim) {
@@ -392,6 +407,7 @@ inline PairLayout pair_layout(int dim) {
     L.stage_bytes = kPairHalfX + kPairQBlock;
   }
   L.smem_bytes = L.q_bytes + L.stages * L.stage_bytes + kMergeBytes + 512 + 1024;
+  L.flags = 0;
   return L;
 }
 
@@ -407,6 +423,7 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* qbuf = smem;
   uint8_t* stages = smem + L.q_bytes;
   uint8_t* merge_buf = stages + L.stages * L.stage_bytes;
+  float* xn_s = reinterpret_cast<float*>(merge_buf + BQ * kMaxK * 8);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(merge_buf + kMergeBytes);
   uint64_t* empty_bar = full_bar + kPairMaxStages;
   uint64_t* tfull_bar = empty_bar + kPairMaxStages;
@@ -519,6 +536,7 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int sub = warp & 3;
     const int half = (warp - 4) >> 2;
     const int r = sub * 32 + lane;
+    const int et = threadIdx.x - 128;          // 0..255: the tile column whose ||x||^2 this thread stages
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -529,17 +547,23 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int my_rows = item.q_rows - row_off;   // valid query rows of this CTA (may be <= 0)
       TopK<K> best;
       best.init();
+      xn_s[et] = load_tile_xnorm(xnorm, item, 0, num_tiles, et, metric_ip);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int t = 0; t < num_tiles; ++t) {
+        const float xn_next = load_tile_xnorm(xnorm, item, t + 1, num_tiles, et, metric_ip);   // lands during the scan
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
-        scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
-                          xnorm + item.b_row0 + col_base, col_base, metric_ip, best);
+        if (!(L.flags & 1))
+          scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
+                            xn_s + (t & 1) * BX + half * (BX / 2), col_base, metric_ip, best);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+        xn_s[((t + 1) & 1) * BX + et] = xn_next;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // slot (t+1)&1 complete; slot t&1 no longer read
       }
       merge_halves_and_store<K>(best, half, r, my_rows, static_cast<long>(item.out_row0) + row_off + r,
                                 (metric_ip || r >= my_rows) ? 0.f
@@ -557,11 +581,24 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// Experiment switches of the pair kernel (fp_knn_set_flags; 0 in production):
+//   bit 0  epilogue warps skip the scan (main-loop speed alone; results are garbage)
+//   bit 1  stream the queries with the bank even when they would fit in shared memory
+int g_knn_flags = 0;
+
 template <int K>
 int launch_knn_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* items, int num_items,
                     int dim, const float* qnorm, const float* xnorm, int metric_ip, int k_out,
                     float* out_d, int64_t* out_i, cudaStream_t stream) {
-  const PairLayout L = pair_layout(dim);
+  PairLayout L = pair_layout(dim);
+  if ((g_knn_flags & 2) && L.q_resident) {
+    L.q_resident = 0;
+    L.stages = 6;
+    L.q_bytes = 0;
+    L.stage_bytes = kPairHalfX + kPairQBlock;
+    L.smem_bytes = L.stages * L.stage_bytes + kMergeBytes + 512 + 1024;
+  }
+  L.flags = g_knn_flags;
   static bool configured[64] = {};
   if (per_device_once(configured)) {
     FP_CUDA_CHECK(cudaFuncSetAttribute(knn_pair_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -678,6 +715,8 @@ __global__ void knn_merge_kernel(const float* __restrict__ part_d, const int64_t
 }
 
 }  // namespace
+
+void knn_set_flags(int flags) { g_knn_flags = flags; }
 
 int knn_items_per_rows(int rows) { return (rows + BQ - 1) / BQ; }
 

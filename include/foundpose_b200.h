@@ -175,6 +175,10 @@ int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const floa
                              int dim, const fp_knn_item* items, int num_items, int metric, int k,
                              float* out_d, int64_t* out_i, void* stream);
 
+/* Experiment switches of the pair kernel (tools/k4_probe.py): bit 0 = skip the epilogue scan, bit 1 = stream the
+ * queries instead of keeping them resident.  0 (default) in production. */
+int fp_knn_set_flags(int flags);
+
 /* ---- crop stage in front of the extractor ------------------------- */
 /* warp_image x2 + array_to_tensor + calc_2d_box for B instances (scripts/infer.py:427-456,
  * utils/misc.py:458-519, cv2.remap semantics).  images: [num_images, src_h, src_w, channels]

@@ -77,19 +77,26 @@ def descriptor_stage(pipe: Any, crop: int, image: torch.Tensor, mask: torch.Tens
     return res
 
 
-def retrieval_stage(index: Any, out: Any, crop: int, q_points: torch.Tensor, q_desc: torch.Tensor, top_k: int
+def retrieval_stage(index: Any, engine: Any, crop: int, q_points: torch.Tensor, q_desc: torch.Tensor, top_k: int
                     ) -> Dict:
-    """Stages 2 and 3 for one crop, oracle fed with the descriptors the CUDA path matched.
+    """Stages 2 and 3 for one crop of a RetrievalEngine run, oracle fed with the descriptors the CUDA path matched.
 
-    q_points [n,2] fp32 CPU, q_desc [n, d_padded] fp32 CPU (the fp16 rows the kernels read, widened).
+    q_points [n,2] fp32 CPU, q_desc [n, d_padded] fp32 CPU (the fp16 rows the kernels read, widened).  Chained:
+      2   tf-idf + cosine scores + top-N     vs otemplate.tfidf_matching on q_desc
+      3a  the two 1-NN searches per pair     vs oknn.knn_l2 on (q_desc, the template's rows): ids equal wherever the
+                                             oracle's fp64 margin > MARGIN (asserted), distances within DIST_RTOL
+      3b  cycle distance, top-k, gathers     vs ocorresp.cyclic_buddies_from_ids on the CUDA path's OWN 1-NN ids:
+                                             2D ids, 3D ids and distances bit-exact (asserted)
     """
     ix = _index_cpu(index)
+    out = engine.out
     n = q_points.shape[0]
     topn = out.template_ids.shape[1]
     res: Dict[str, Any] = {"n_queries": n}
     if n == 0:
-        res.update(templates_equal=bool((out.count[crop] == 0).all().item()), pairs=0, pairs_sure=0, pairs_exact=0,
-                   corr_agree=1.0)
+        assert bool((out.count[crop] == 0).all().item())
+        res.update(templates_equal=True, templates_sure=True, pairs=0, pairs_exact=0, nn_checked=0, nn_sure_frac=1.0,
+                   nn_equal_frac=1.0, corr_agree=1.0)
         return res
     ids, scores, tfidf, cos = otemplate.tfidf_matching(
         q_desc, ix["centroids"], ix["idfs"], ix["template_descs"], topn, index.tfidf_knn_k, index.tfidf_knn_metric,
@@ -103,9 +110,10 @@ def retrieval_stage(index: Any, out: Any, crop: int, q_points: torch.Tensor, q_d
     res["templates_sure"] = gap > 1e-5
     res["template_score_err"] = float((ours_scores - cos[ours_ids]).abs().max())
     res["tfidf_err"] = float((out.query_tfidf[crop].cpu() - tfidf).abs().max())
-    pairs = sure = exact = 0
+    pairs = exact = 0
+    nn_total = nn_sure = nn_equal = 0
     agree = total = 0
-    dist_err = 0.0
+    nn_dist_err = 0.0
     for j in range(topn):
         t = int(ours_ids[j])
         r0, r1 = int(ix["tpl_off"][t]), int(ix["tpl_off"][t + 1])
@@ -113,29 +121,48 @@ def retrieval_stage(index: Any, out: Any, crop: int, q_points: torch.Tensor, q_d
         if r1 == r0:
             assert cnt == 0, "a template without bank rows must yield no correspondences"
             continue
+        p = crop * topn + j
         rows = index.bank16[r0:r1].float().cpu()
-        q_ids, o_ids, dists, conf = ocorresp.cyclic_buddies_matching(q_points, q_desc, rows, top_k)
+        g_q2o = engine.q2o_i[p * engine.stride: p * engine.stride + n, 0].cpu()
+        g_o2q = engine.o2q_i[p * engine.max_p: p * engine.max_p + (r1 - r0), 0].cpu()
+        g_q2o_d = engine.q2o_d[p * engine.stride: p * engine.stride + n, 0].cpu()
+        # 3a: the two 1-NN searches
+        for ours_i, (qq, xx), ours_d in ((g_q2o, (q_desc, rows), g_q2o_d), (g_o2q, (rows, q_desc), None)):
+            rd, ri = oknn.knn_l2(qq, xx, 1)
+            sure_m = oknn.topk_margin(qq, xx, 1)[:, 0] > MARGIN
+            same = ours_i == ri[:, 0]
+            assert bool(same[sure_m].all()), f"crop {crop} template {t}: 1-NN ids differ outside the tie margin"
+            nn_total += same.numel(); nn_sure += int(sure_m.sum()); nn_equal += int(same.sum())
+            if ours_d is not None:
+                err = ((ours_d - rd[:, 0]).abs() / rd[:, 0].clamp_min(1e-6)).max()
+                nn_dist_err = max(nn_dist_err, float(err))
+        assert nn_dist_err <= DIST_RTOL, f"1-NN distances off by {nn_dist_err:.2e} relative"
+        # 3b: cyclic buddies from the CUDA path's own ids
+        q_ids, o_ids, dists, conf = ocorresp.cyclic_buddies_from_ids(q_points, g_q2o, g_o2q, top_k)
         feat_ids = o_ids + r0
         if ix["feat_perm"] is not None:
             feat_ids = ix["feat_perm"][feat_ids]
-        m1 = oknn.topk_margin(q_desc, rows, 1).min()
-        m2 = oknn.topk_margin(rows, q_desc, 1).min()
-        is_sure = bool(min(float(m1), float(m2)) > MARGIN)
         g_q = out.query_ids[crop, j, :cnt].cpu()
         g_v = out.vertex_ids[crop, j, :cnt].cpu()
-        same = cnt == q_ids.shape[0] and torch.equal(g_q, q_ids) and torch.equal(g_v, feat_ids)
+        g_d = out.dists[crop, j, :cnt].cpu()
+        same = cnt == q_ids.shape[0] and torch.equal(g_q, q_ids) and torch.equal(g_v, feat_ids) \
+            and torch.equal(g_d, dists)
+        assert same, f"crop {crop} template {t}: cyclic-buddies outputs differ from the oracle on the same 1-NN ids"
+        assert torch.allclose(out.scores[crop, j, :cnt].cpu(), conf, equal_nan=True)
+        assert torch.equal(out.coord_2d[crop, j, :cnt].cpu(), q_points[q_ids])
         pairs += 1
-        sure += int(is_sure)
         exact += int(same)
-        if is_sure:
-            assert same, f"crop {crop} template {t}: correspondence ids differ although every 1-NN margin > {MARGIN}"
-            g_d = out.dists[crop, j, :cnt].cpu()
-            dist_err = max(dist_err, float((g_d - dists).abs().max()))
-        if cnt == q_ids.shape[0]:
-            agree += int(((g_q == q_ids) & (g_v == feat_ids)).sum())
-        total += q_ids.shape[0]
-    res.update(pairs=pairs, pairs_sure=sure, pairs_exact=exact, corr_agree=agree / max(total, 1),
-               cyc_dist_err=dist_err)
+        # full-oracle comparison of the pair (1-NN + cycle by the oracle), as a rate
+        o_q, o_o, _, _ = ocorresp.cyclic_buddies_matching(q_points, q_desc, rows, top_k)
+        o_f = o_o + r0
+        if ix["feat_perm"] is not None:
+            o_f = ix["feat_perm"][o_f]
+        if cnt == o_q.shape[0]:
+            agree += int(((g_q == o_q) & (g_v == o_f)).sum())
+        total += o_q.shape[0]
+    res.update(pairs=pairs, pairs_exact=exact, nn_checked=nn_total, nn_sure_frac=nn_sure / max(nn_total, 1),
+               nn_equal_frac=nn_equal / max(nn_total, 1), nn_dist_rel_err=nn_dist_err,
+               corr_agree=agree / max(total, 1))
     return res
 
 

@@ -21,6 +21,12 @@ def cyclic_buddies_matching(query_points: torch.Tensor, query_features: torch.Te
     """utils/corresp_util.py:34-70."""
     query2obj = oknn.knn_l2(query_features, object_features, 1)[1].flatten()
     obj2query = oknn.knn_l2(object_features, query_features, 1)[1].flatten()
+    return cyclic_buddies_from_ids(query_points, query2obj, obj2query, top_k)
+
+
+def cyclic_buddies_from_ids(query_points: torch.Tensor, query2obj: torch.Tensor, obj2query: torch.Tensor, top_k: int
+                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """utils/corresp_util.py:50-70: the part after the two 1-NN searches (cycle, 2D distance, top-k, scores)."""
     u1 = query_points
     cycle_ids = obj2query[query2obj]
     u2 = query_points[cycle_ids]
