@@ -341,10 +341,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 // Arrive on the leader CTA's copy of a barrier (local arrive when executed by the leader).
+// Default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) issues it: what the
+// consumer orders against is tcgen05 state (guarded by tcgen05.fence::before_thread_sync in front of the arrive),
+// not generic-proxy memory.  The `.release.cluster` form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in
+// front of the arrive - 20% of the k-NN pair kernel's stall samples (profiles/r02_k4_pair_ncu.md).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) &
-                                                                                   kPeerBitMask)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
 // ----------------------------------------------------------------------------

@@ -33,7 +33,8 @@ constexpr int BX = 256;   // bank rows per tile (128 x 256 x 16 UMMA: 96 B/clk o
 constexpr int BKK = 64;   // K elements per stage
 constexpr int kStages = 4;
 constexpr int kMaxK = 16;
-constexpr uint32_t kXnBytes = 2 * BX * 4;          // ||x||^2 of the current and the next tile
+constexpr int kXnTiles = 4;                        // bank tiles per staged group of ||x||^2 (one barrier per group)
+constexpr uint32_t kXnBytes = 2 * kXnTiles * BX * 4;   // ||x||^2 of the current and the next group of tiles
 constexpr uint32_t kMergeBytes = BQ * kMaxK * 8 + kXnBytes;   // (dist, idx) lists of the second column half + xn_s
 constexpr uint32_t kQStage = BQ * BKK * 2;
 constexpr uint32_t kXStage = BX * BKK * 2;
@@ -81,9 +82,23 @@ struct TopK {
 // load per 32-column chunk on the critical path of every tile cost more than the chunk's arithmetic),
 // `col_base` = index of the half's first column relative to the item's segment.
 // L2: ||x||^2 - 2<q,x> (||q||^2 is added once per item); IP: -<q,x>.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 template <int K>
-__device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, const float* __restrict__ xn,
+__device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32_t xn /* shared address */,
                                                int col_base, int metric_ip, TopK<K>& best) {
+  // dist = scale * <q,x> + ||x||^2 with scale = -2 (L2) or -1 (IP, where the staged norms are zero): one FFMA per
+  // candidate, no per-element select on the metric.
+  const float scale = metric_ip ? -1.0f : -2.0f;
 #pragma unroll 1
   for (int c = 0; c < BX / 64; ++c) {
     uint32_t v[32];
@@ -94,23 +109,17 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, const 
       if (c * 32 + 32 <= ncols) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!metric_ip) n4 = *reinterpret_cast<const float4*>(xn + c * 32 + g * 4);
-          dist[g * 4 + 0] = metric_ip ? -__uint_as_float(v[g * 4 + 0]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 0]), n4.x);
-          dist[g * 4 + 1] = metric_ip ? -__uint_as_float(v[g * 4 + 1]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 1]), n4.y);
-          dist[g * 4 + 2] = metric_ip ? -__uint_as_float(v[g * 4 + 2]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 2]), n4.z);
-          dist[g * 4 + 3] = metric_ip ? -__uint_as_float(v[g * 4 + 3]) : fmaf(-2.0f, __uint_as_float(v[g * 4 + 3]), n4.w);
+          const float4 n4 = lds_f4(xn + (c * 32 + g * 4) * 4);
+          dist[g * 4 + 0] = fmaf(scale, __uint_as_float(v[g * 4 + 0]), n4.x);
+          dist[g * 4 + 1] = fmaf(scale, __uint_as_float(v[g * 4 + 1]), n4.y);
+          dist[g * 4 + 2] = fmaf(scale, __uint_as_float(v[g * 4 + 2]), n4.z);
+          dist[g * 4 + 3] = fmaf(scale, __uint_as_float(v[g * 4 + 3]), n4.w);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int col = c * 32 + i;
-          float dv = INFINITY;
-          if (col < ncols) {
-            const float dot = __uint_as_float(v[i]);
-            dv = metric_ip ? -dot : fmaf(-2.0f, dot, xn[col]);
-          }
-          dist[i] = dv;
+          dist[i] = col < ncols ? fmaf(scale, __uint_as_float(v[i]), lds_f1(xn + col * 4)) : INFINITY;
         }
       }
       if constexpr (K == 1) {
@@ -155,12 +164,22 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, const 
   }
 }
 
-// ||x||^2 of a tile's 256 bank columns: one column per epilogue thread (et = 0..255), zero past the segment.
-__device__ __forceinline__ float load_tile_xnorm(const float* __restrict__ xnorm, const KnnItem& item, int tile,
-                                                 int num_tiles, int et, int metric_ip) {
-  const int col = tile * BX + et;
-  if (metric_ip || tile >= num_tiles || col >= item.b_rows) return 0.f;
-  return __ldg(xnorm + item.b_row0 + col);
+// ||x||^2 of a group of kXnTiles bank tiles (kXnTiles * 256 columns): epilogue thread et = 0..255 stages columns
+// et, et + 256, ... of the group; zero past the segment (and for the inner-product metric).
+struct XnGroup { float v[kXnTiles]; };
+__device__ __forceinline__ XnGroup load_group_xnorm(const float* __restrict__ xnorm, const KnnItem& item, int group,
+                                                    int et, int metric_ip) {
+  XnGroup g;
+#pragma unroll
+  for (int i = 0; i < kXnTiles; ++i) {
+    const int col = (group * kXnTiles + i) * BX + et;
+    g.v[i] = (metric_ip || col >= item.b_rows) ? 0.f : __ldg(xnorm + item.b_row0 + col);
+  }
+  return g;
+}
+__device__ __forceinline__ void store_group_xnorm(float* slot, const XnGroup& g, int et) {
+#pragma unroll
+  for (int i = 0; i < kXnTiles; ++i) slot[i * BX + et] = g.v[i];
 }
 
 // Merges the two column halves of an item through shared memory (their index ranges interleave tile by tile ->
@@ -314,22 +333,27 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       const int num_tiles = (item.b_rows + BX - 1) / BX;
       TopK<K> best;
       best.init();
-      xn_s[et] = load_tile_xnorm(xnorm, item, 0, num_tiles, et, metric_ip);
+      store_group_xnorm(xn_s, load_group_xnorm(xnorm, item, 0, et, metric_ip), et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      XnGroup xn_next;
       for (int t = 0; t < num_tiles; ++t) {
-        const float xn_next = load_tile_xnorm(xnorm, item, t + 1, num_tiles, et, metric_ip);   // lands during the scan
+        const int grp = t / kXnTiles, tg = t % kXnTiles;
+        if (tg == 0) xn_next = load_group_xnorm(xnorm, item, grp + 1, et, metric_ip);   // lands during the scans
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
         scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
-                          xn_s + (t & 1) * BX + half * (BX / 2), col_base, metric_ip, best);
+                          smem_u32(xn_s + ((grp & 1) * kXnTiles + tg) * BX + half * (BX / 2)), col_base, metric_ip,
+                          best);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        xn_s[((t + 1) & 1) * BX + et] = xn_next;
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // slot (t+1)&1 complete; slot t&1 no longer read
+        if (tg == kXnTiles - 1) {
+          store_group_xnorm(xn_s + ((grp + 1) & 1) * kXnTiles * BX, xn_next, et);
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // next group's slot complete; this group's no longer read
+        }
       }
       merge_halves_and_store<K>(best, half, r, item.q_rows, static_cast<long>(item.out_row0) + r,
                                 (metric_ip || r >= item.q_rows) ? 0.f : qnorm[static_cast<long>(item.q_row0) + r],
@@ -547,23 +571,28 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int my_rows = item.q_rows - row_off;   // valid query rows of this CTA (may be <= 0)
       TopK<K> best;
       best.init();
-      xn_s[et] = load_tile_xnorm(xnorm, item, 0, num_tiles, et, metric_ip);
+      store_group_xnorm(xn_s, load_group_xnorm(xnorm, item, 0, et, metric_ip), et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      XnGroup xn_next;
       for (int t = 0; t < num_tiles; ++t) {
-        const float xn_next = load_tile_xnorm(xnorm, item, t + 1, num_tiles, et, metric_ip);   // lands during the scan
+        const int grp = t / kXnTiles, tg = t % kXnTiles;
+        if (tg == 0) xn_next = load_group_xnorm(xnorm, item, grp + 1, et, metric_ip);   // lands during the scans
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
         if (!(L.flags & 1))
           scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
-                            xn_s + (t & 1) * BX + half * (BX / 2), col_base, metric_ip, best);
+                            smem_u32(xn_s + ((grp & 1) * kXnTiles + tg) * BX + half * (BX / 2)), col_base, metric_ip,
+                            best);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        xn_s[((t + 1) & 1) * BX + et] = xn_next;
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // slot (t+1)&1 complete; slot t&1 no longer read
+        if (tg == kXnTiles - 1) {
+          store_group_xnorm(xn_s + ((grp + 1) & 1) * kXnTiles * BX, xn_next, et);
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // next group's slot complete; this group's no longer read
+        }
       }
       merge_halves_and_store<K>(best, half, r, my_rows, static_cast<long>(item.out_row0) + row_off + r,
                                 (metric_ip || r >= my_rows) ? 0.f
