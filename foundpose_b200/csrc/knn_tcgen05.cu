@@ -34,7 +34,8 @@ constexpr int BKK = 64;   // K elements per stage
 constexpr int kStages = 4;
 constexpr int kMaxK = 16;
 constexpr int kXnTiles = 4;                        // bank tiles per staged group of ||x||^2 (one barrier per group)
-constexpr uint32_t kXnBytes = 2 * kXnTiles * BX * 4;   // ||x||^2 of the current and the next group of tiles
+constexpr int kXnSlot = kXnTiles * BX + kXnTiles * (BX / 32);   // floats per slot: the norms + the min of every 32-column chunk
+constexpr uint32_t kXnBytes = 2 * kXnSlot * 4;         // ||x||^2 of the current and the next group of tiles
 constexpr uint32_t kMergeBytes = BQ * kMaxK * 8 + kXnBytes;   // (dist, idx) lists of the second column half + xn_s
 constexpr uint32_t kQStage = BQ * BKK * 2;
 constexpr uint32_t kXStage = BX * BKK * 2;
@@ -95,6 +96,7 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 
 template <int K>
 __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32_t xn /* shared address */,
+                                               uint32_t xn_min /* shared address: min ||x||^2 per 32 columns */,
                                                int col_base, int metric_ip, TopK<K>& best) {
   // dist = scale * <q,x> + ||x||^2 with scale = -2 (L2) or -1 (IP, where the staged norms are zero): one FFMA per
   // candidate, no per-element select on the metric.
@@ -107,6 +109,21 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32
     if (c * 32 < ncols) {
       float dist[32];
       if (c * 32 + 32 <= ncols) {
+        // Safe prefilter on the raw inner products: every distance of the chunk is >= scale * max<q,x> + min||x||^2
+        // (scale < 0; fmaf is monotone in each argument, so the bound also holds for the rounded values).  When
+        // that bound cannot enter the list - almost always once the list has warmed up - the chunk costs one
+        // 3-input max tree instead of 32 FFMA + the norm loads + the scan.
+        float m[11];
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+          m[i] = fmaxf(fmaxf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
+        m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+        m[0] = fmaxf(fmaxf(m[0], m[1]), m[2]);
+        m[3] = fmaxf(fmaxf(m[3], m[4]), m[5]);
+        m[6] = fmaxf(fmaxf(m[6], m[7]), m[8]);
+        m[9] = fmaxf(m[9], m[10]);
+        const float smax = fmaxf(fmaxf(fmaxf(m[0], m[3]), m[6]), m[9]);
+        if (fmaf(scale, smax, lds_f1(xn_min + c * 4)) >= best.d[K - 1]) continue;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 n4 = lds_f4(xn + (c * 32 + g * 4) * 4);
@@ -177,9 +194,17 @@ __device__ __forceinline__ XnGroup load_group_xnorm(const float* __restrict__ xn
   }
   return g;
 }
+// Also stores the minimum of every 32-column chunk (a warp's 32 consecutive columns are exactly one chunk) behind
+// the norms: slot[kXnTiles * BX + tile * 8 + chunk].
 __device__ __forceinline__ void store_group_xnorm(float* slot, const XnGroup& g, int et) {
 #pragma unroll
-  for (int i = 0; i < kXnTiles; ++i) slot[i * BX + et] = g.v[i];
+  for (int i = 0; i < kXnTiles; ++i) {
+    slot[i * BX + et] = g.v[i];
+    float mn = g.v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((et & 31) == 0) slot[kXnTiles * BX + i * (BX / 32) + (et >> 5)] = mn;
+  }
 }
 
 // Merges the two column halves of an item through shared memory (their index ranges interleave tile by tile ->
@@ -343,15 +368,16 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
         scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
-                          smem_u32(xn_s + ((grp & 1) * kXnTiles + tg) * BX + half * (BX / 2)), col_base, metric_ip,
-                          best);
+                          smem_u32(xn_s + (grp & 1) * kXnSlot + tg * BX + half * (BX / 2)),
+                          smem_u32(xn_s + (grp & 1) * kXnSlot + kXnTiles * BX + tg * (BX / 32) + half * (BX / 64)),
+                          col_base, metric_ip, best);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         if (tg == kXnTiles - 1) {
-          store_group_xnorm(xn_s + ((grp + 1) & 1) * kXnTiles * BX, xn_next, et);
+          store_group_xnorm(xn_s + ((grp + 1) & 1) * kXnSlot, xn_next, et);
           asm volatile("bar.sync 1, 256;" ::: "memory");   // next group's slot complete; this group's no longer read
         }
       }
@@ -582,15 +608,16 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int col_base = t * BX + half * (BX / 2);
         if (!(L.flags & 1))
           scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
-                            smem_u32(xn_s + ((grp & 1) * kXnTiles + tg) * BX + half * (BX / 2)), col_base, metric_ip,
-                            best);
+                            smem_u32(xn_s + (grp & 1) * kXnSlot + tg * BX + half * (BX / 2)),
+                            smem_u32(xn_s + (grp & 1) * kXnSlot + kXnTiles * BX + tg * (BX / 32) + half * (BX / 64)),
+                            col_base, metric_ip, best);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         if (tg == kXnTiles - 1) {
-          store_group_xnorm(xn_s + ((grp + 1) & 1) * kXnTiles * BX, xn_next, et);
+          store_group_xnorm(xn_s + ((grp + 1) & 1) * kXnSlot, xn_next, et);
           asm volatile("bar.sync 1, 256;" ::: "memory");   // next group's slot complete; this group's no longer read
         }
       }

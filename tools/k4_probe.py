@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--crops", type=int, default=64)
     ap.add_argument("--dim", type=int, default=384)
     ap.add_argument("--variants", type=str, default="pair,pair_noscan,pair_stream,one_cta,pair_l2")
-    ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--iters", type=int, default=4)
     args = ap.parse_args()
     from foundpose_b200 import _native
     from foundpose_b200.utils import knn_util
@@ -40,16 +40,43 @@ def main():
     index = knn_util.KNN.from_packed(bank, bn, k=5, metric="l2")
     small = knn_util.KNN.from_packed(bank[:65536], bn[:65536], k=5, metric="l2")   # 50 MB: stays in L2
 
+    import threading
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(0)
+    except Exception:
+        pynvml = handle = None
+    power = {}
+
     def time_it(fn, flops):
         fn()
         torch.cuda.synchronize()
+        samples, stop = [], threading.Event()
+
+        def sample():
+            while not stop.is_set() and pynvml is not None:
+                samples.append((pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM),
+                                pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0))
+                stop.wait(0.02)
+
+        th = threading.Thread(target=sample, daemon=True)
+        th.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.iters):
             fn()
         e1.record()
         torch.cuda.synchronize()
+        stop.set()
+        th.join()
         ms = e0.elapsed_time(e1) / args.iters
+        if samples:
+            samples.sort()
+            power["sm_mhz_median"] = samples[len(samples) // 2][0]
+            power["watts_median"] = sorted(w for _, w in samples)[len(samples) // 2]
         return ms, flops / (ms * 1e-3) / 1e12
 
     def one_cta():
@@ -81,7 +108,8 @@ def main():
         else:
             continue
         lib.fp_knn_set_flags(0)
-        print(json.dumps({"variant": v, "ms": round(ms, 3), "tflops": round(tf, 1), "nq": nq, "bank_rows": F, "dim": d}))
+        print(json.dumps({"variant": v, "ms": round(ms, 3), "tflops": round(tf, 1), "nq": nq, "bank_rows": F, "dim": d,
+                          **power}))
 
 
 if __name__ == "__main__":
