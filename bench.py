@@ -751,19 +751,23 @@ def measure_extras(lib, pipe, index, dev, hbm_peak: float, B: int) -> dict:
     try:
         eng = pipe.engine
         for _ in range(2):
-            _native.bow_scores(index.template_descs, index.desc_norm, eng.tfidf, eng.cos)
+            eng.score_templates()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            _native.bow_scores(index.template_descs, index.desc_norm, eng.tfidf, eng.cos)
+            eng.score_templates()
         e1.record()
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 10 * 1e-3
         nbytes = index.template_descs.numel() * 4
         out["bow"] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                      "frac": nbytes / t / 1e9 / hbm_peak, "kernel_ms": t * 1e3, "descriptor_bytes": nbytes,
-                      "crops": B, "templates": int(index.template_descs.shape[0])}
+                      "frac": nbytes / t / 1e9 / hbm_peak, "stage_ms": t * 1e3, "descriptor_bytes": nbytes,
+                      "crops": B, "templates": int(index.template_descs.shape[0]),
+                      "path": "tensor cores (split-fp16 inner-product top-N through the k-NN kernel)" if eng.bow_tensor
+                      else "fp32 CUDA cores", "bytes_read": int(index.split_descs().numel() * 2) if eng.bow_tensor else nbytes,
+                      "note": "whole scoring stage (query split + search + merge) for one micro-batch; algorithmic "
+                              "bytes = T*W*4 of fp32 template descriptors"}
     except Exception as e:
         out["bow"] = {"error": repr(e)}
     try:

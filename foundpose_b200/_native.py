@@ -176,6 +176,18 @@ def convert_rows_f16(x: torch.Tensor, l2_normalize: bool = False, out: Optional[
     return out
 
 
+def split_rows_f16(x: torch.Tensor, pattern: int, l2_normalize: bool, scale: float,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows, dim] -> f16 [rows, 3*dim] hi/lo split (fp_split_rows_f16)."""
+    require_cuda(x, "x", torch.float32)
+    rows, dim = x.shape
+    if out is None:
+        out = torch.empty((rows, 3 * dim), dtype=torch.float16, device=x.device)
+    call("fp_split_rows_f16", ptr(x), ptr(out), _l(rows), _i(dim), _i(pattern), _i(int(l2_normalize)), _f(scale),
+         stream_ptr(x.device))
+    return out
+
+
 def row_sqnorm_f16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     require_cuda(x, "x", torch.float16)
     rows, dim = x.shape

@@ -188,6 +188,12 @@ int fp_row_sqnorm_f16(const void* x_f16, float* out, int64_t rows, int dim, void
                             static_cast<cudaStream_t>(stream));
 }
 
+int fp_split_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int pattern, int l2_normalize,
+                      float scale, void* stream) {
+  return fp::split_rows_f16(x, static_cast<__half*>(y_f16), rows, dim, pattern, l2_normalize, scale,
+                            static_cast<cudaStream_t>(stream));
+}
+
 int fp_pca_project(const void* x_f16, const void* components_f16, const float* bias, int M, int D,
                    int d, float* out_f32, void* out_f16, void* stream) {
   if (M <= 0) return 0;

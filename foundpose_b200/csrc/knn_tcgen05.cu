@@ -606,7 +606,14 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
-        if (!(L.flags & 1))
+        if (L.flags & 4) {   // experiment: TMEM reads only
+          for (int c = 0; c < BX / 64; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * BX + half * (BX / 2) + c * 32, v);
+            tmem_ld_wait();
+            if (__uint_as_float(v[lane]) == 1.2345e30f) best.d[0] = 0.f;   // keep the load alive
+          }
+        } else if (!(L.flags & 1))
           scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
                             smem_u32(xn_s + (grp & 1) * kXnSlot + tg * BX + half * (BX / 2)),
                             smem_u32(xn_s + (grp & 1) * kXnSlot + kXnTiles * BX + tg * (BX / 32) + half * (BX / 64)),
@@ -640,6 +647,7 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // Experiment switches of the pair kernel (fp_knn_set_flags; 0 in production):
 //   bit 0  epilogue warps skip the scan (main-loop speed alone; results are garbage)
 //   bit 1  stream the queries with the bank even when they would fit in shared memory
+//   bit 2  epilogue warps only read the accumulators out of TMEM (no arithmetic)
 int g_knn_flags = 0;
 
 template <int K>
@@ -707,6 +715,40 @@ __global__ void convert_rows_kernel(const float* __restrict__ x, __half* __restr
       inv = 1.0f / sqrtf(s);
     }
     for (int i = lane; i < dim; i += 32) y[row * dim + i] = __float2half_rn(xr[i] * inv);
+  }
+}
+
+// fp32 rows -> THREE fp16 column blocks whose pairwise products reproduce the fp32 inner product on the tensor
+// cores: x = hi + lo (hi = fp16(x), lo = fp16(x - hi): 22 significant bits), and
+//     <a, b> ~= <a_hi, b_hi> + <a_lo, b_hi> + <a_hi, b_lo>       (the lo.lo term is below fp32 resolution)
+// pattern 0 writes [hi | lo | hi] (bank side), pattern 1 writes [hi | hi | lo] (query side), so ONE contraction
+// over 3W columns yields the three terms.  Rows are optionally L2-normalised first (cosine similarity,
+// utils/template_util.py:160-164: zero rows stay zero, like x / max(||x||, eps)) and multiplied by `scale` (a
+// power of two that lifts the lo parts out of the fp16 subnormal range).  One warp per row.
+__global__ void split_rows_kernel(const float* __restrict__ x, __half* __restrict__ y, long rows, int dim,
+                                  int pattern, int l2_normalize, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long row = blockIdx.x * static_cast<long>(wpb) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long>(gridDim.x) * wpb) {
+    const float* xr = x + row * dim;
+    float mul = scale;
+    if (l2_normalize) {
+      float s = 0.f;
+      for (int i = lane; i < dim; i += 32) s = fmaf(xr[i], xr[i], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mul = s > 0.f ? scale / sqrtf(s) : 0.f;
+    }
+    __half* yr = y + row * 3L * dim;
+    for (int i = lane; i < dim; i += 32) {
+      const float v = xr[i] * mul;
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      yr[i] = hi;
+      yr[dim + i] = pattern == 0 ? lo : hi;
+      yr[2 * dim + i] = pattern == 0 ? hi : lo;
+    }
   }
 }
 
@@ -827,6 +869,18 @@ int convert_rows_f16(const float* x, __half* y, long rows, int dim, int l2_norma
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   ProfScope prof(PROF_FEATURE, stream, static_cast<double>(rows) * dim * 6);
   convert_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, rows, dim, l2_normalize);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int split_rows_f16(const float* x, __half* y, long rows, int dim, int pattern, int l2_normalize, float scale,
+                   cudaStream_t stream) {
+  if (rows == 0) return 0;
+  FP_REQUIRE(pattern == 0 || pattern == 1, "split_rows: pattern must be 0 (bank side) or 1 (query side)");
+  long blocks = (rows + 7) / 8;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(rows) * dim * 10);
+  split_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, rows, dim, pattern, l2_normalize, scale);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

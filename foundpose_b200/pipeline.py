@@ -28,6 +28,10 @@ from foundpose_b200 import _native
 # Descriptor rows are padded to a multiple of 128 columns everywhere: the PCA GEMM writes N % 128 == 0 columns
 # (PCAProjector.device_state) and the bank rows it is matched against must have the same width.
 DESC_PAD = 128
+# Bag-of-words scores on the tensor cores: both sides are scaled by 2^10 before the hi/lo split (keeps the lo parts
+# of unit-vector entries out of the fp16 subnormals); inner products come back multiplied by 2^20.
+BOW_SCALE = 1024.0
+BOW_CHUNK_ROWS = 256      # templates per k-NN item (one bank tile): T / 256 SMs stream the descriptors in parallel
 
 
 def _pad_cols(x: torch.Tensor, mult: int = DESC_PAD) -> torch.Tensor:
@@ -85,6 +89,10 @@ class ObjectIndex:
             self.centroid_sqnorm = _native.row_sqnorm_f16(self.centroids16)
         if getattr(repre, "feat_cluster_idfs", None) is not None:
             self.idfs = repre.feat_cluster_idfs.to(dev, torch.float32).contiguous()
+        self.desc_split16: Optional[torch.Tensor] = None     # built on first use by a RetrievalEngine
+        self.idfs_finite = True
+        if self.idfs is not None:
+            self.idfs_finite = bool(torch.isfinite(self.idfs).all().item())
         if getattr(repre, "template_descs", None) is not None:
             self.template_descs = repre.template_descs.to(dev, torch.float32).contiguous()
             self.desc_norm = _native.row_norm_f32(self.template_descs)
@@ -99,6 +107,13 @@ class ObjectIndex:
     @property
     def num_words(self) -> int:
         return int(self.centroids16.shape[0])
+
+    def split_descs(self) -> torch.Tensor:
+        """Unit-norm template descriptors as fp16 [T, 3W] = [hi | lo | hi] * 2^10 (fp_split_rows_f16): the index of
+        the tensor-core bag-of-words scoring."""
+        if self.desc_split16 is None:
+            self.desc_split16 = _native.split_rows_f16(self.template_descs, 0, True, BOW_SCALE)
+        return self.desc_split16
 
 
 def get_object_index(repre: Any, device: torch.device) -> ObjectIndex:
@@ -161,6 +176,24 @@ class RetrievalEngine:
         self.cos = torch.empty((batch, index.num_templates), dtype=f32, device=dev)
         self.top_scores = torch.empty((batch, self.topn), dtype=f32, device=dev)
         self.top_ids = torch.empty((batch, self.topn), dtype=i64, device=dev)
+        # Template scoring (utils/template_util.py:160-176) as ONE inner-product top-N search on the tensor cores:
+        # cos(q, d) = <q/||q||, d/||d||> with both unit vectors split into fp16 hi + lo parts (fp32-accurate), the
+        # k-NN kernel's epilogue keeps the N best templates per crop, so the [B, T] score matrix never exists.
+        # Kept on the fp32 CUDA-core path: N > 16, non-finite idfs (the reference's NaN scores) and
+        # callers that want the full score matrix (`full_scores`).
+        self.full_scores = False
+        self.bow_tensor = self.topn <= 16 and index.idfs_finite
+        if self.bow_tensor:
+            T, W = index.num_templates, index.num_words
+            self.bow_chunks = (T + BOW_CHUNK_ROWS - 1) // BOW_CHUNK_ROWS
+            self.bow_qblocks = _native.knn_num_items(batch)
+            self.bow_items = _native.new_knn_items(self.bow_qblocks * self.bow_chunks, dev)
+            _native.knn_items_split(self.bow_items, batch, 0, T, self.bow_chunks, BOW_CHUNK_ROWS)
+            self.bow_q16 = torch.empty((batch, 3 * W), dtype=torch.float16, device=dev)
+            q_pad = self.bow_qblocks * 128
+            self.bow_part_d = torch.empty((self.bow_chunks * q_pad, self.topn), dtype=f32, device=dev)
+            self.bow_part_i = torch.full((self.bow_chunks * q_pad, self.topn), -1, dtype=i64, device=dev)
+            index.split_descs()
         self.per_q = (stride + 127) // 128
         self.per_p = (self.max_p + 127) // 128
         self.items_q2o = _native.new_knn_items(npairs * self.per_q, dev)
@@ -182,6 +215,22 @@ class RetrievalEngine:
             coord_2d=torch.zeros((batch, self.topn, k, 2), dtype=f32, device=dev),
             coord_3d=torch.zeros((batch, self.topn, k, 3), dtype=f32, device=dev),
             query_tfidf=self.tfidf, cos_sims=self.cos, word_ids=self.word_i, word_dists=self.word_d)
+
+    def score_templates(self) -> None:
+        """self.tfidf [B, W] -> top-N template ids / cosine scores (utils/template_util.py:160-176)."""
+        ix = self.index
+        if self.bow_tensor:
+            _native.split_rows_f16(self.tfidf, 1, True, BOW_SCALE, out=self.bow_q16)
+            _native.knn_search_items(self.bow_q16, None, ix.split_descs(), None, self.bow_items,
+                                     self.bow_qblocks * self.bow_chunks, 1, self.topn, self.bow_part_d,
+                                     self.bow_part_i)
+            _native.knn_merge(self.bow_part_d, self.bow_part_i, self.bow_chunks, self.bow_qblocks * 128, self.batch,
+                              self.topn, BOW_CHUNK_ROWS, ix.num_templates, True, self.top_scores, self.top_ids)
+            self.top_scores.mul_(1.0 / (BOW_SCALE * BOW_SCALE))
+        if self.full_scores or not self.bow_tensor:
+            _native.bow_scores(ix.template_descs, ix.desc_norm, self.tfidf, self.cos)
+            if not self.bow_tensor:
+                _native.topk_rows(self.cos, self.topn, self.top_scores, self.top_ids)
 
     def match(self, feat16: torch.Tensor, points: torch.Tensor, q_count: torch.Tensor) -> MatchOutputs:
         """feat16 [B*stride, dpad] f16 query descriptors, points [B, stride, 2], q_count int32 [B]."""
@@ -205,8 +254,7 @@ class RetrievalEngine:
             torch.sub(1.0, self.word_d, out=self.word_d)
         _native.calc_tfidf(self.word_i, self.word_d, self.q_start, q_count, ix.idfs, ix.tfidf_soft_assign,
                            ix.tfidf_soft_sigma_squared, True, self.tfidf)
-        _native.bow_scores(ix.template_descs, ix.desc_norm, self.tfidf, self.cos)
-        _native.topk_rows(self.cos, self.topn, self.top_scores, self.top_ids)
+        self.score_templates()
         # K2 / K3: 1-NN in both directions for every (crop, retrieved template) pair.
         _native.build_pair_items(self.top_ids, self.topn, ix.tpl_off, self.q_start, q_count, self.stride,
                                  self.max_p, self.items_q2o, self.items_o2q)

@@ -125,6 +125,15 @@ int fp_convert_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int 
 /* out[r] = ||x[r]||^2 (fp32) of f16 rows; the ||x||^2 term of faiss's L2 expansion. */
 int fp_row_sqnorm_f16(const void* x_f16, float* out, int64_t rows, int dim, void* stream);
 
+/* fp32 rows [rows, dim] -> f16 rows [rows, 3*dim] holding the split x = hi + lo as [hi | lo | hi] (pattern 0, index
+ * side) or [hi | hi | lo] (pattern 1, query side): one inner-product search over the 3*dim columns then evaluates
+ * <a,b> to fp32 accuracy on the tensor cores.  Rows are optionally L2-normalised first (zero rows stay zero) and
+ * multiplied by `scale` (use a power of two, e.g. 1024, to keep the lo parts out of the f16 subnormals; the inner
+ * products come back multiplied by scale_a * scale_b).  Used for the bag-of-words cosine scores
+ * torch.nn.functional.cosine_similarity(template_descs, query_tfidf) of utils/template_util.py:160-164. */
+int fp_split_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int pattern, int l2_normalize,
+                      float scale, void* stream);
+
 /* ---- PCA projection ------------------------------------------------------------------------
  * out = x . components^T + bias, bias = -(mean . components^T)  (sklearn PCA.transform with
  * whiten=False as called at utils/projector_util.py:66-69).  x f16 [M,D], components f16 [d,D],

@@ -288,6 +288,7 @@ def test_engine_cosine_visual_word_metric(soft):
         template_desc_opts=opts)
     index = pipeline.ObjectIndex(repre, torch.device("cuda"))
     engine = pipeline.RetrievalEngine(index, B, nq, 5, 20)
+    engine.full_scores = True          # also produce the [B, T] score matrix (fp32 path) for the comparison below
     qs = [synthetic.make_query_features(nq, d, feat, seed=40 + b) for b in range(B)]
     pts = torch.rand(B, nq, 2, device="cuda") * 100
     cnt = torch.full((B,), nq, dtype=torch.int32, device="cuda")
