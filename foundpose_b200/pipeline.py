@@ -179,10 +179,10 @@ class RetrievalEngine:
         # Template scoring (utils/template_util.py:160-176) as ONE inner-product top-N search on the tensor cores:
         # cos(q, d) = <q/||q||, d/||d||> with both unit vectors split into fp16 hi + lo parts (fp32-accurate), the
         # k-NN kernel's epilogue keeps the N best templates per crop, so the [B, T] score matrix never exists.
-        # Kept on the fp32 CUDA-core path: N > 16, non-finite idfs (the reference's NaN scores) and
+        # Kept on the fp32 CUDA-core path: N > 16, a vocabulary whose 3W is not a multiple of 64, non-finite idfs (the reference's NaN scores) and
         # callers that want the full score matrix (`full_scores`).
         self.full_scores = False
-        self.bow_tensor = self.topn <= 16 and index.idfs_finite
+        self.bow_tensor = self.topn <= 16 and index.idfs_finite and (3 * index.num_words) % 64 == 0
         if self.bow_tensor:
             T, W = index.num_templates, index.num_words
             self.bow_chunks = (T + BOW_CHUNK_ROWS - 1) // BOW_CHUNK_ROWS

@@ -126,6 +126,37 @@ def make_vit_state_dict(arch: VitArch, seed: int = 0, depth: Optional[int] = Non
     return sd
 
 
+def make_vit_state_dict_realistic(arch: VitArch, seed: int = 0, depth: Optional[int] = None
+                                  ) -> Dict[str, torch.Tensor]:
+    """Random weights with the statistics that make PRETRAINED DINOv2 checkpoints numerically harder than a
+    trunc-normal init (there is no network to fetch a real checkpoint):
+
+      * "massive activation" channels: three residual channels sit at magnitude ~80-300 in every token (written by
+        the patch-embed bias and re-inforced by fc2 biases), two orders of magnitude above the rest;
+      * LayerScale gammas log-uniform in [1e-5, 1] (DINOv2 initialises them at 1e-5 and training spreads them);
+      * LayerNorm gains spread over [0.1, 4];
+      * peaked attention: q / k projections scaled so that the logits have a standard deviation of ~10 (the row
+        maximum moves by far more than 2^8 between key blocks: the lazy-rescale path of the attention kernel);
+      * fc1 pre-activations with a standard deviation of ~3 (GELU well outside its linear region).
+    """
+    sd = make_vit_state_dict(arch, seed=seed, depth=depth)
+    g = _gen(seed + 7919)
+    d = arch.embed_dim
+    n_blocks = arch.depth if depth is None else depth
+    outliers = torch.randperm(d, generator=g)[:3]
+    sd["patch_embed.proj.bias"][outliers] = torch.tensor([300.0, -150.0, 80.0])
+    for i in range(n_blocks):
+        p = f"blocks.{i}."
+        for ls in ("ls1.gamma", "ls2.gamma"):
+            sd[p + ls] = torch.exp(torch.empty(d).uniform_(math.log(1e-5), 0.0, generator=g))
+        for nm in ("norm1.weight", "norm2.weight"):
+            sd[p + nm] = torch.exp(torch.empty(d).uniform_(math.log(0.1), math.log(4.0), generator=g))
+        sd[p + "attn.qkv.weight"][: 2 * d] *= 4.0          # q and k rows: logits ~ 16x larger
+        sd[p + "mlp.fc1.weight"] *= 3.0
+        sd[p + "mlp.fc2.bias"][outliers] += torch.tensor([20.0, -10.0, 5.0])
+    return sd
+
+
 def make_crops(batch: int, size: Tuple[int, int] = (420, 420), seed: int = 0) -> torch.Tensor:
     """B x 3 x H x W float32 in [0, 1) (scripts/infer.py:398 scales uint8 images the same way)."""
     w, h = size

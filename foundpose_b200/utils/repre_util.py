@@ -13,7 +13,7 @@ from typing import Any, Dict, List, NamedTuple, Optional
 
 import torch
 
-from foundpose_b200.utils import logging, projector_util
+from foundpose_b200.utils import logging, projector_util, structs
 from foundpose_b200.utils.misc import tensor_to_array
 
 logger: logging.Logger = logging.get_logger()
@@ -123,7 +123,13 @@ def load_object_repre(repre_dir: str, tensor_device: str = "cuda",
             repre_dict["feat_vis_projectors"].append(projector_util.projector_from_tensordict(projector))
     repre_dict["template_cameras_cam_from_model"] = []
     if load_fields is None or "template_cameras_cam_from_model" in load_fields:
-        repre_dict["template_cameras_cam_from_model"] = list(object_dict.get("template_cameras_cam_from_model", []))
+        # Same return structure as the reference (:179-190): PinholePlaneCameraModel objects.
+        for camera in object_dict.get("template_cameras_cam_from_model", []):
+            repre_dict["template_cameras_cam_from_model"].append(structs.PinholePlaneCameraModel(
+                f=tuple(float(v) for v in torch.as_tensor(camera["f"]).flatten().tolist()),
+                c=tuple(float(v) for v in torch.as_tensor(camera["c"]).flatten().tolist()),
+                width=int(camera["width"]), height=int(camera["height"]),
+                T_world_from_eye=torch.as_tensor(camera["T_world_from_eye"]).to(torch.float64).numpy()))
     if load_fields is None or "template_desc_opts" in load_fields:
         if object_dict.get("template_desc_opts") is not None:
             repre_dict["template_desc_opts"] = TemplateDescOpts(**dict(object_dict["template_desc_opts"]))

@@ -123,3 +123,55 @@ def test_extractor_errors():
         ext(torch.rand(1, 3, 50, 56, device="cuda"))
     with pytest.raises(ValueError):      # no CPU fallback
         ext(torch.rand(1, 3, 56, 56))
+
+
+@pytest.mark.parametrize("tag", ["vits14-reg", "vitl14"])
+def test_vit_numerics_with_pretrained_like_statistics(tag):
+    """fp16 operands under DINOv2-checkpoint-like statistics (synthetic.make_vit_state_dict_realistic: residual
+    outlier channels at 80-300, LayerScale 1e-5..1, LayerNorm gains 0.1..4, attention logits with std ~10 - the
+    lazy O-rescale path of the attention kernel -, fc1 pre-activations with std ~3): outputs must be finite and
+    within 1e-2 relative Frobenius error / 0.9995 per-token cosine of the fp32 oracle."""
+    from foundpose_b200.utils import dinov2_utils
+    from oracle import vit as ovit
+
+    arch = synthetic.VIT_ARCHS[tag]
+    layer = 9
+    sd = synthetic.make_vit_state_dict_realistic(arch, seed=5, depth=layer + 1)
+    images = synthetic.make_crops(2, (420, 420), seed=6)
+    name = f"dinov2_version={tag}_stride=14_facet=token_layer={layer}_norm=1"
+    ext = dinov2_utils.DinoFeatureExtractor(name, state_dict=sd).to("cuda")
+    # the unnormalised block output too: the final LayerNorm would hide a saturated residual stream
+    ext.apply_norm = False
+    raw = ext(images.cuda())["feature_maps"].cpu()
+    ext.apply_norm = True
+    fm = ext(images.cuda())["feature_maps"].cpu()
+    assert torch.isfinite(raw).all() and torch.isfinite(fm).all()
+    ref_raw = ovit.extract(sd, arch, images, layer=layer, num_blocks=layer + 1, apply_norm=False)["feature_maps"]
+    ref = ovit.extract(sd, arch, images, layer=layer, num_blocks=layer + 1)["feature_maps"]
+    assert ref_raw.abs().max().item() > 50.0                      # the outlier channels really are there
+    a = fm.permute(0, 2, 3, 1).reshape(-1, arch.embed_dim)
+    b = ref.permute(0, 2, 3, 1).reshape(-1, arch.embed_dim)
+    cos = torch.nn.functional.cosine_similarity(a, b, dim=1)
+    print(f"{tag} (pretrained-like statistics): rel err raw {_rel(raw, ref_raw):.2e}, normed {_rel(fm, ref):.2e}, "
+          f"min cos {cos.min().item():.6f}, max |x| {ref_raw.abs().max().item():.0f}")
+    assert _rel(raw, ref_raw) <= 1e-2 and _rel(fm, ref) <= 1e-2
+    assert cos.min().item() >= 0.9995
+
+
+def test_checkpoint_file_is_loaded_through_the_env_hook(tmp_path, monkeypatch):
+    """FOUNDPOSE_DINOV2_WEIGHTS=<file in the official checkpoint layout> (utils/dinov2_utils.py:82-84 downloads
+    the same state_dict): the extractor built from the file == the extractor given the state_dict directly."""
+    from foundpose_b200.utils import dinov2_utils, feature_util
+
+    arch = synthetic.VIT_ARCHS["vits14-reg"]
+    sd = synthetic.make_vit_state_dict(arch, seed=3)               # all 12 blocks + mask_token, as published
+    path = tmp_path / "dinov2_vits14_reg4_pretrain.pth"
+    torch.save(sd, str(path))
+    monkeypatch.setenv("FOUNDPOSE_DINOV2_WEIGHTS", str(path))
+    name = "dinov2_version=vits14-reg_stride=14_facet=token_layer=9_norm=1"
+    from_file = feature_util.make_feature_extractor(name).to("cuda")
+    monkeypatch.delenv("FOUNDPOSE_DINOV2_WEIGHTS")
+    direct = dinov2_utils.DinoFeatureExtractor(name, state_dict=sd).to("cuda")
+    assert set(from_file.model.state_dict()) == set(direct.model.state_dict())
+    images = synthetic.make_crops(1, (420, 420), seed=4).cuda()
+    assert torch.equal(from_file(images)["feature_maps"], direct(images)["feature_maps"])
