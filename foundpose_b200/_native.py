@@ -414,7 +414,7 @@ def cyclic_buddies(points, q_start, q_count, q2o, o2q, top_ids, topn, tpl_off, f
 class VitConfig(ctypes.Structure):
     _fields_ = [("embed_dim", ctypes.c_int), ("num_heads", ctypes.c_int), ("num_blocks", ctypes.c_int),
                 ("num_register_tokens", ctypes.c_int), ("patch_size", ctypes.c_int), ("img_h", ctypes.c_int),
-                ("img_w", ctypes.c_int)]
+                ("img_w", ctypes.c_int), ("fuse_layernorm", ctypes.c_int)]
 
 
 class VitWeights(ctypes.Structure):
@@ -425,7 +425,7 @@ class VitWeights(ctypes.Structure):
 class VitBlockWeights(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("norm1_w", "norm1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1", "norm2_w", "norm2_b",
-                 "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+                 "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2", "qkv_colsum", "fc1_colsum")]
 
 
 def vit_create(cfg: VitConfig, weights: VitWeights, blocks, max_batch: int) -> ctypes.c_void_p:

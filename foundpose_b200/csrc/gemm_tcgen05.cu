@@ -69,7 +69,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_store32(const GemmParams& p, int row, int n0,
-                                                 const uint32_t (&r)[32]) {
+                                                 const uint32_t (&r)[32], float& s1, float& s2) {
   // One thread owns 32 consecutive output columns [n0, n0+32) of one row.
   if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
     __half* dst = p.out_f16 + static_cast<size_t>(row) * p.ld_f16 + n0;
@@ -112,12 +112,13 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, int row, i
       x.w += g.w * (__uint_as_float(r[j * 4 + 3]) + b.w);
       *reinterpret_cast<float4*>(dst + j * 4) = x;
     }
-  } else if constexpr (EPI == EPI_PATCH_F32) {
+  } else if constexpr (EPI == EPI_PATCH_F32 || EPI == EPI_PATCH_LN_F32) {
     const int b_img = row / p.patches_per_img;
     const int pidx = row - b_img * p.patches_per_img;
     const size_t drow = static_cast<size_t>(b_img) * p.tokens_per_img + p.tok_off + pidx;
     float* dst = p.out_f32 + drow * p.ld_f32 + n0;
     const float* pos = p.pos + static_cast<size_t>(pidx) * p.N + n0;
+    float v[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
@@ -128,6 +129,29 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, int row, i
       x.z = __uint_as_float(r[j * 4 + 2]) + b.z + e.z;
       x.w = __uint_as_float(r[j * 4 + 3]) + b.w + e.w;
       *reinterpret_cast<float4*>(dst + j * 4) = x;
+      v[j * 4 + 0] = x.x; v[j * 4 + 1] = x.y; v[j * 4 + 2] = x.z; v[j * 4 + 3] = x.w;
+    }
+    if constexpr (EPI == EPI_PATCH_LN_F32) {
+      // fp16 copy + partial sums for the first block's LayerNorm (once per forward: plain stores).
+      __half* d16 = p.x16 + drow * p.ld_x16 + n0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        __half2 h0 = __floats2half2_rn(v[j * 8 + 0], v[j * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(v[j * 8 + 2], v[j * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(v[j * 8 + 4], v[j * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(v[j * 8 + 6], v[j * 8 + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(d16 + j * 8) = pk;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        s1 += v[i];
+        s2 = fmaf(v[i], v[i], s2);
+      }
     }
   } else {  // EPI_BIAS_F32 (+ optional fp16 copy)
     float* dst = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + n0;
@@ -275,7 +299,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + col0, r);
         tmem_ld_wait();
-        if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r);
+        float unused1 = 0.f, unused2 = 0.f;
+        if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r, unused1, unused2);
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -306,18 +331,25 @@ struct Gemm2Cfg {
   // The residual epilogue stages its output through shared memory for TMA reduce-add stores
   // (8 epilogue warps x 2 buffers x 4 KB), paid for with one pipeline stage.
   static constexpr bool kTmaReduce = (EPI == EPI_RESID_F32);
+  // Residual epilogue that also feeds the next LayerNorm: x is read-modify-written through shared memory (the SM
+  // has to see the updated rows to emit their fp16 copy and partial sums), 3 staging buffers per epilogue warp.
+  static constexpr bool kResidLn = (EPI == EPI_RESID_LN_F32);
+  // LayerNorm statistics applied to the accumulator rows (consumer side of the fusion).
+  static constexpr bool kLnFold = (EPI == EPI_LN_BIAS_F16 || EPI == EPI_LN_BIAS_GELU_F16);
+  static constexpr bool kGelu = (EPI == EPI_BIAS_GELU_F16 || EPI == EPI_LN_BIAS_GELU_F16);
   // fp16 outputs (qkv, fc1) leave through smem + TMA stores as well: per-thread 16-byte global
   // stores of a row-per-thread fragment (half sectors, 32 rows per instruction) were measured to
   // cost 70-100 us per GEMM; the TMA writes whole 128-byte lines asynchronously.
-  static constexpr bool kTmaStore16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
-  static constexpr bool kStaged = kTmaReduce || kTmaStore16;
-  static constexpr int kStages = kStaged ? 5 : 6;
+  static constexpr bool kTmaStore16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kLnFold);
+  static constexpr bool kStaged = kTmaReduce || kTmaStore16 || kResidLn;
+  static constexpr int kStages = kResidLn ? 4 : (kStaged ? 5 : 6);
   static constexpr int BN = 256;                       // output tile columns (pair)
   static constexpr uint32_t kABytes = BM * BK * 2;     // 16 KB: this CTA's 128 rows of A
   static constexpr uint32_t kBBytes = 128 * BK * 2;    // 16 KB: this CTA's half of the B tile
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 512;           // 2 accumulators x 256 columns
-  static constexpr uint32_t kStagingBytes = kStaged ? kEpilogueWarps * 2 * 4096 : 0;
+  static constexpr uint32_t kWarpStaging = kResidLn ? 3 * 4096 : 2 * 4096;   // bytes per epilogue warp
+  static constexpr uint32_t kStagingBytes = kStaged ? kEpilogueWarps * kWarpStaging : 0;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
 
@@ -345,7 +377,8 @@ __device__ __forceinline__ void tma_store_wait_read() {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
+                const GemmParams p) {
   using Cfg = Gemm2Cfg<EPI>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int BN = Cfg::BN;
@@ -377,7 +410,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&tfull_bar[a], 1);                // multicast tcgen05.commit
       mbar_init(&tempty_bar[a], 2 * kEpilogueWarps);   // leader: epilogue warps of both CTAs
     }
-    if constexpr (Cfg::kTmaReduce) {
+    if constexpr (Cfg::kTmaReduce || Cfg::kResidLn) {
       for (int i = 0; i < 2 * kEpilogueWarps; ++i) mbar_init(&ld_bar[i], 1);
     }
     fence_barrier_init();
@@ -458,13 +491,13 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n_blk = t - m_blk * num_n;
       const int row0 = m_blk * 2 * BM + static_cast<int>(rank) * BM + sub * 32;
       const int row = row0 + lane;
-      if constexpr (Cfg::kTmaReduce) {
+      if constexpr (Cfg::kTmaReduce || Cfg::kResidLn) {
         // Read-modify-write mode: the x blocks of the first two chunks are requested while the tile's MMAs run.
-        if (resid_rmw && lane == 0) {
+        if ((resid_rmw || Cfg::kResidLn) && lane == 0) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             if (c == 0) tma_store_wait_read<1>(); else tma_store_wait_read<0>();   // the store that last read it
-            uint8_t* buf = staging + (warp - 4) * 8192 + c * 4096;
+            uint8_t* buf = staging + (warp - 4) * Cfg::kWarpStaging + c * 4096;
             uint64_t* bar = &ld_bar[(warp - 4) * 2 + c];
             mbar_arrive_expect_tx(bar, 4096);
             tma_load_2d(buf, &tmC, bar, n_blk * BN + half * (BN / 2) + c * 32, row0);
@@ -474,8 +507,88 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
-      if constexpr (Cfg::kTmaStore16) {
+      if constexpr (Cfg::kResidLn) {
+        // x_new = x + gamma * (acc + bias), read-modify-written through shared memory (x block fetched by the TMA
+        // while the tile's MMAs run, plain TMA store back), PLUS what the next LayerNorm needs: the fp16 copy of
+        // the new rows (64-column blocks through a third staging buffer) and sum x / sum x^2 of this thread's 128
+        // columns, written to stats_out[row, n_blk * 2 + half] - one slot per 128 columns, summed in a fixed
+        // order by the consumer (deterministic, no atomics).
+        float s1 = 0.f, s2 = 0.f;
+        uint8_t* wbuf = staging + (warp - 4) * Cfg::kWarpStaging;
+        uint8_t* xbuf = wbuf + 8192;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int col0 = half * (BN / 2) + c * 32;
+          const int n0 = n_blk * BN + col0;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + col0, r);
+          tmem_ld_wait();
+          uint8_t* buf = wbuf + (c & 1) * 4096;
+          mbar_wait(&ld_bar[(warp - 4) * 2 + (c & 1)], ld_phase[c & 1]);
+          ld_phase[c & 1] ^= 1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j * 4));
+            float4* cell = reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4));
+            float4 y = *cell;
+            y.x += g.x * (__uint_as_float(r[j * 4 + 0]) + b.x);
+            y.y += g.y * (__uint_as_float(r[j * 4 + 1]) + b.y);
+            y.z += g.z * (__uint_as_float(r[j * 4 + 2]) + b.z);
+            y.w += g.w * (__uint_as_float(r[j * 4 + 3]) + b.w);
+            *cell = y;
+            s1 += (y.x + y.y) + (y.z + y.w);
+            s2 = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, s2))));
+            __half2 h0 = __floats2half2_rn(y.x, y.y);
+            __half2 h1 = __floats2half2_rn(y.z, y.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            // 64-column fp16 block (128-byte rows, 128B swizzle): 16-byte chunk (c&1)*4 + j/2, half j&1
+            *reinterpret_cast<uint2*>(xbuf + lane * 128 + ((((c & 1) * 4 + (j >> 1)) ^ (lane & 7)) << 4) +
+                                      (j & 1) * 8) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, n0, row0);
+            if (c & 1) tma_store_2d(&tmD, xbuf, n_blk * BN + half * (BN / 2) + (c >> 1) * 64, row0);
+            tma_store_commit();
+            if (c + 2 < BN / 64) {   // x block of chunk c + 2 into the buffer just stored from
+              tma_store_wait_read<0>();
+              uint64_t* bar = &ld_bar[(warp - 4) * 2 + (c & 1)];
+              mbar_arrive_expect_tx(bar, 4096);
+              tma_load_2d(buf, &tmC, bar, n0 + 64, row0);
+            }
+          }
+          __syncwarp();   // xbuf / buf are rewritten by the next chunk only after lane 0 has waited
+        }
+        if (row < p.M) {
+          float2* st = reinterpret_cast<float2*>(p.stats_out) +
+                       static_cast<size_t>(row) * (p.N / 128) + n_blk * 2 + half;
+          *st = make_float2(s1, s2);
+        }
+      } else if constexpr (Cfg::kTmaStore16) {
         // Two 32 x 64 fp16 blocks per warp: TMEM -> bias (+GELU) -> 128B-swizzled smem -> TMA store.
+        // LN fold: the accumulator row is LN-normalised here, out = rstd (acc - mu colsum) + bias.
+        float ln_a = 1.f, ln_g = 0.f;
+        if constexpr (Cfg::kLnFold) {
+          ln_a = 0.f;
+          if (row < p.M) {
+            const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + static_cast<size_t>(row) * p.ln_slots;
+            float t1 = 0.f, t2 = 0.f;
+            for (int t = 0; t < p.ln_slots; ++t) {
+              const float2 v2 = __ldg(st + t);
+              t1 += v2.x;
+              t2 += v2.y;
+            }
+            const float inv_d = 1.0f / static_cast<float>(p.ln_dim);
+            const float mu = t1 * inv_d;
+            const float var = fmaxf(fmaf(-mu, mu, t2 * inv_d), 0.f);
+            ln_a = rsqrtf(var + p.ln_eps);
+            ln_g = -ln_a * mu;
+          }
+        }
 #pragma unroll 1
         for (int blk = 0; blk < 2; ++blk) {
           const int col0 = half * (BN / 2) + blk * 64;
@@ -494,13 +607,22 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
-            if (p.bias != nullptr) {
+            if constexpr (Cfg::kLnFold) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 8 + 4));
+              const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j * 8));
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j * 8 + 4));
+              v[0] = fmaf(ln_a, v[0], fmaf(ln_g, c0.x, b0.x)); v[1] = fmaf(ln_a, v[1], fmaf(ln_g, c0.y, b0.y));
+              v[2] = fmaf(ln_a, v[2], fmaf(ln_g, c0.z, b0.z)); v[3] = fmaf(ln_a, v[3], fmaf(ln_g, c0.w, b0.w));
+              v[4] = fmaf(ln_a, v[4], fmaf(ln_g, c1.x, b1.x)); v[5] = fmaf(ln_a, v[5], fmaf(ln_g, c1.y, b1.y));
+              v[6] = fmaf(ln_a, v[6], fmaf(ln_g, c1.z, b1.z)); v[7] = fmaf(ln_a, v[7], fmaf(ln_g, c1.w, b1.w));
+            } else if (p.bias != nullptr) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 8));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 8 + 4));
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-            if constexpr (EPI == EPI_BIAS_GELU_F16) {
+            if constexpr (Cfg::kGelu) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
             }
@@ -523,6 +645,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       } else {
+      float ps1 = 0.f, ps2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         const int col0 = half * (BN / 2) + c * 32;
@@ -584,7 +707,14 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           }
         } else {
-          if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r);
+          if (row < p.M) epilogue_store32<EPI>(p, row, n_blk * BN + col0, r, ps1, ps2);
+        }
+      }
+      if constexpr (EPI == EPI_PATCH_LN_F32) {
+        if (row < p.M) {   // one slot per 128 columns of the DESTINATION token row
+          const int b_img = row / p.patches_per_img;
+          const size_t drow = static_cast<size_t>(b_img) * p.tokens_per_img + p.tok_off + (row - b_img * p.patches_per_img);
+          reinterpret_cast<float2*>(p.stats_out)[drow * (p.N / 128) + n_blk * 2 + half] = make_float2(ps1, ps2);
         }
       }
       }
@@ -611,9 +741,23 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int EPI>
 int launch_2sm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<EPI>;
-  CUtensorMap tmC = tmA;   // only read by the TMA reduce-add epilogue
-  if (Cfg::kTmaReduce) {
+  CUtensorMap tmC = tmA;   // only read by the staged epilogues
+  CUtensorMap tmD = tmA;   // fp16 copy of the residual rows (EPI_RESID_LN_F32)
+  if (Cfg::kTmaReduce || Cfg::kResidLn) {
     if (make_tma_2d_f32_sw128(&tmC, p.out_f32, p.M, p.N, p.ld_f32, 32) != 0) return 3;
+  }
+  if (Cfg::kResidLn) {
+    FP_REQUIRE(p.x16 != nullptr && p.stats_out != nullptr && p.ld_x16 % 8 == 0,
+               "gemm_tn: EPI_RESID_LN_F32 needs x16 (ld %% 8 == 0) and stats_out");
+    if (make_tma_2d_f16(&tmD, p.x16, p.M, p.N, p.ld_x16, 32, 64) != 0) return 3;
+  }
+  if (Cfg::kLnFold) {
+    FP_REQUIRE(p.ln_stats != nullptr && p.ln_colsum != nullptr && p.bias != nullptr && p.ln_slots > 0 &&
+               p.ln_dim > 0, "gemm_tn: EPI_LN_* needs ln_stats, ln_colsum, bias, ln_slots and ln_dim");
+  }
+  if (EPI == EPI_PATCH_LN_F32) {
+    FP_REQUIRE(p.x16 != nullptr && p.stats_out != nullptr && p.ld_x16 % 8 == 0,
+               "gemm_tn: EPI_PATCH_LN_F32 needs x16 (ld %% 8 == 0) and stats_out");
   }
   if (Cfg::kTmaStore16) {
     FP_REQUIRE(p.ld_f16 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_f16) & 15) == 0,
@@ -628,7 +772,7 @@ int launch_2sm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
   const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / Cfg::BN);
   int clusters = num_tiles < num_sms() / 2 ? num_tiles : num_sms() / 2;
   ProfScope prof(PROF_GEMM, stream, 2.0 * p.M * p.N * p.K);
-  gemm2_tn_kernel<EPI><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  gemm2_tn_kernel<EPI><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmD, p);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -702,9 +846,15 @@ int gemm_tn(int epi, const __half* A, int lda, const __half* B, int ldb, const G
       case EPI_RESID_F32: return launch_2sm<EPI_RESID_F32>(tmA, tmB, p, stream);
       case EPI_PATCH_F32: return launch_2sm<EPI_PATCH_F32>(tmA, tmB, p, stream);
       case EPI_BIAS_F32: return launch_2sm<EPI_BIAS_F32>(tmA, tmB, p, stream);
+      case EPI_LN_BIAS_F16: return launch_2sm<EPI_LN_BIAS_F16>(tmA, tmB, p, stream);
+      case EPI_LN_BIAS_GELU_F16: return launch_2sm<EPI_LN_BIAS_GELU_F16>(tmA, tmB, p, stream);
+      case EPI_RESID_LN_F32: return launch_2sm<EPI_RESID_LN_F32>(tmA, tmB, p, stream);
+      case EPI_PATCH_LN_F32: return launch_2sm<EPI_PATCH_LN_F32>(tmA, tmB, p, stream);
       default: set_last_error("gemm_tn: unknown epilogue %d", epi); return 1;
     }
   }
+  FP_REQUIRE(epi <= EPI_BIAS_F32, "gemm_tn: the LayerNorm-fused epilogues need N %% 256 == 0 and M > 256 "
+             "(pair kernel); got M=%d N=%d", p.M, p.N);
   switch (epi) {
     case EPI_BIAS_F16: return launch_bn<EPI_BIAS_F16>(bn, tmA, tmB, p, stream);
     case EPI_BIAS_GELU_F16: return launch_bn<EPI_BIAS_GELU_F16>(bn, tmA, tmB, p, stream);

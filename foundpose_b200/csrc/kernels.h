@@ -16,6 +16,15 @@ enum GemmEpilogue : int {
   EPI_RESID_F32 = 2,      // out_f32 += gamma * (acc + bias)              (proj/fc2 + LayerScale + residual)
   EPI_PATCH_F32 = 3,      // token stream row remap + bias + pos-embed    (patch embedding)
   EPI_BIAS_F32 = 4,       // out_f32 = acc + bias (+ fp16 copy)           (PCA projection)
+  // LayerNorm fused into the GEMMs around it (layers/block.py:63,75 + the Linear that follows):
+  //   LN(x) W^T + b = rstd * (x W'^T - mu * colsum(W')) + b'   with W' = W diag(gamma), b' = b + W beta,
+  // so the CONSUMER runs on the raw fp16 copy of the residual rows and applies (mu, rstd) per row in its epilogue,
+  // and the PRODUCER of the residual rows (patch embed / proj / fc2 epilogue) emits that fp16 copy and the
+  // per-row partial sums (sum x, sum x^2 per 128 columns) the statistics are built from.
+  EPI_LN_BIAS_F16 = 5,       // out_f16 = rstd_m * (acc - mu_m * colsum_n) + bias_n               (norm1 + qkv)
+  EPI_LN_BIAS_GELU_F16 = 6,  // out_f16 = gelu_erf(rstd_m * (acc - mu_m * colsum_n) + bias_n)     (norm2 + fc1 + act)
+  EPI_RESID_LN_F32 = 7,      // EPI_RESID_F32 (x read-modify-write through shared memory) + x16 + row partial sums
+  EPI_PATCH_LN_F32 = 8,      // EPI_PATCH_F32 + x16 + row partial sums
 };
 
 struct GemmParams {
@@ -32,6 +41,18 @@ struct GemmParams {
   int tok_off = 0;
   const float* pos = nullptr;    // [patches_per_img, N] fp32
   int flags = 0;                 // A/B tuning switches (see gemm_force_1sm)
+  // EPI_LN_*: statistics of the A rows.  ln_stats [M, ln_slots, 2] partial (sum, sum of squares) per 128 columns
+  // of the ln_dim-wide rows, ln_colsum [N] = sum_k W'[n, k] of the fp16 weights actually multiplied.
+  const float* ln_stats = nullptr;
+  int ln_slots = 0;
+  const float* ln_colsum = nullptr;
+  int ln_dim = 0;
+  float ln_eps = 1e-6f;
+  // EPI_RESID_LN_F32 / EPI_PATCH_LN_F32: fp16 copy of the rows written to out_f32 and their partial sums
+  // stats_out [rows, N / 128, 2] (row index = row of out_f32).
+  __half* x16 = nullptr;
+  int ld_x16 = 0;
+  float* stats_out = nullptr;
 };
 
 int gemm_pick_bn(int M, int N);
@@ -45,7 +66,8 @@ int umma_probe(const __half* A, const __half* B, float* out, int b_mn_major, cud
 int patchify_normalize(const float* img, __half* out, int B, int H, int W, int ps, int Kpad,
                        cudaStream_t stream);
 int init_special_tokens(float* x, const float* cls_pos, const float* reg, int B, int ntok, int R,
-                        int D, cudaStream_t stream);
+                        int D, cudaStream_t stream, __half* x16 = nullptr, float* stats = nullptr,
+                        int stat_slots = 0);
 int layernorm_f16(const float* x, __half* y, const float* w, const float* b, int M, int D, float eps,
                   cudaStream_t stream);
 int final_norm_tokens(const float* x, const float* w, const float* b, float* out_tok,

@@ -29,6 +29,10 @@ struct VitHandle {
   __half* attn = nullptr;     // [max_batch*ntok, D]
   __half* hidden = nullptr;   // [max_batch*ntok, 4D]
   float* facet_x = nullptr;   // [max_batch*ntok, D]     only for key/query/value facets
+  // LayerNorm-fused mode (cfg.fuse_layernorm): fp16 copy of the residual stream (the GEMM operand instead of xn)
+  // and per-row partial (sum, sum of squares) per 128 columns, both written by the producing epilogues.
+  bool fused_ln = false;
+  float* stats = nullptr;     // [max_batch*ntok, D/128, 2]
 };
 
 namespace {
@@ -65,6 +69,13 @@ int fp_vit_create(const fp_vit_config* cfg, const fp_vit_weights* weights,
              "Input image size %dx%d is not a multiple of patch size %d", cfg->img_h, cfg->img_w,
              cfg->patch_size);
   FP_REQUIRE(cfg->num_blocks >= 1 && max_batch >= 1, "fp_vit_create: bad num_blocks/max_batch");
+  FP_REQUIRE(!cfg->fuse_layernorm || cfg->embed_dim % 256 == 0,
+             "fp_vit_create: fuse_layernorm needs embed_dim %% 256 == 0 (got %d)", cfg->embed_dim);
+  if (cfg->fuse_layernorm) {
+    for (int i = 0; i < cfg->num_blocks; ++i)
+      FP_REQUIRE(blocks[i].qkv_colsum != nullptr && blocks[i].fc1_colsum != nullptr,
+                 "fp_vit_create: fuse_layernorm needs qkv_colsum / fc1_colsum of block %d", i);
+  }
   VitHandle* h = new (std::nothrow) VitHandle();
   FP_REQUIRE(h != nullptr, "fp_vit_create: out of host memory");
   h->cfg = *cfg;
@@ -72,6 +83,7 @@ int fp_vit_create(const fp_vit_config* cfg, const fp_vit_weights* weights,
   h->blocks = new fp_vit_block_weights[cfg->num_blocks];
   for (int i = 0; i < cfg->num_blocks; ++i) h->blocks[i] = blocks[i];
   h->max_batch = max_batch;
+  h->fused_ln = cfg->fuse_layernorm != 0;
   h->P = (cfg->img_h / cfg->patch_size) * (cfg->img_w / cfg->patch_size);
   h->ntok = 1 + cfg->num_register_tokens + h->P;
   const int k = 3 * cfg->patch_size * cfg->patch_size;
@@ -88,6 +100,7 @@ int fp_vit_create(const fp_vit_config* cfg, const fp_vit_weights* weights,
   alloc(reinterpret_cast<void**>(&h->qkv), rows * 3 * D * 2);
   alloc(reinterpret_cast<void**>(&h->attn), rows * D * 2);
   alloc(reinterpret_cast<void**>(&h->hidden), rows * 4 * D * 2);
+  if (h->fused_ln) alloc(reinterpret_cast<void**>(&h->stats), rows * (D / 128) * 2 * 4);
   if (e != cudaSuccess) {
     fp::set_last_error("fp_vit_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     fp_vit_destroy(reinterpret_cast<fp_vit*>(h));
@@ -107,6 +120,7 @@ void fp_vit_destroy(fp_vit* handle) {
   cudaFree(h->attn);
   cudaFree(h->hidden);
   cudaFree(h->facet_x);
+  cudaFree(h->stats);
   delete[] h->blocks;
   delete h;
 }
@@ -132,6 +146,7 @@ int fp_vit_forward(fp_vit* handle, const float* images, int batch, int layer, in
   const int M = batch * h->ntok;
   const float eps = 1e-6f;
   int rc;
+  bool fused = false;   // LayerNorm folded into the GEMMs (h->xn then holds the RAW fp16 residual rows)
 
   // Token preparation: patch embedding (+bias +pos) straight into the token stream, cls/registers.
   if ((rc = fp::patchify_normalize(images, h->patches, batch, h->cfg.img_h, h->cfg.img_w,
@@ -143,23 +158,35 @@ int fp_vit_forward(fp_vit* handle, const float* images, int batch, int layer, in
     p.out_f32 = h->x; p.ld_f32 = D;
     p.patches_per_img = h->P; p.tokens_per_img = h->ntok; p.tok_off = 1 + R;
     p.pos = h->w.pos_patch;
-    if ((rc = fp::gemm_tn(fp::EPI_PATCH_F32, h->patches, h->Kpad,
+    // The pair kernel (the only one with the LayerNorm-fused epilogues) needs more than 256 rows.
+    fused = h->fused_ln;
+    FP_REQUIRE(!fused || batch * h->P > 256,
+               "fp_vit_forward: a handle created with fuse_layernorm needs more than 256 patch rows per call");
+    if (fused) {
+      p.x16 = h->xn; p.ld_x16 = D; p.stats_out = h->stats;
+    }
+    if ((rc = fp::gemm_tn(fused ? fp::EPI_PATCH_LN_F32 : fp::EPI_PATCH_F32, h->patches, h->Kpad,
                           static_cast<const __half*>(h->w.patch_w), h->Kpad, p, stream)) != 0) return rc;
   }
-  if ((rc = fp::init_special_tokens(h->x, h->w.cls_pos, h->w.reg_tokens, batch, h->ntok, R, D,
-                                    stream)) != 0) return rc;
+  if ((rc = fp::init_special_tokens(h->x, h->w.cls_pos, h->w.reg_tokens, batch, h->ntok, R, D, stream,
+                                    fused ? h->xn : nullptr, h->stats, D / 128)) != 0) return rc;
 
   const float* final_src = h->x;
   for (int i = 0; i <= layer; ++i) {
     const fp_vit_block_weights& bw = h->blocks[i];
     // x = x + ls1 * proj(attn(norm1(x)))
-    if ((rc = fp::layernorm_f16(h->x, h->xn, bw.norm1_w, bw.norm1_b, M, D, eps, stream)) != 0) return rc;
+    if (!fused) {
+      if ((rc = fp::layernorm_f16(h->x, h->xn, bw.norm1_w, bw.norm1_b, M, D, eps, stream)) != 0) return rc;
+    }
     {
       fp::GemmParams p;
       p.M = M; p.N = 3 * D; p.K = D;
       p.bias = bw.qkv_b; p.out_f16 = h->qkv; p.ld_f16 = 3 * D;
-      if ((rc = fp::gemm_tn(fp::EPI_BIAS_F16, h->xn, D, static_cast<const __half*>(bw.qkv_w), D, p,
-                            stream)) != 0) return rc;
+      if (fused) {
+        p.ln_stats = h->stats; p.ln_slots = D / 128; p.ln_colsum = bw.qkv_colsum; p.ln_dim = D; p.ln_eps = eps;
+      }
+      if ((rc = fp::gemm_tn(fused ? fp::EPI_LN_BIAS_F16 : fp::EPI_BIAS_F16, h->xn, D,
+                            static_cast<const __half*>(bw.qkv_w), D, p, stream)) != 0) return rc;
     }
     if (i == layer && facet != 0) {
       // key/query/value facet: the hook recomputes qkv from the attention input of this block.
@@ -179,23 +206,35 @@ int fp_vit_forward(fp_vit* handle, const float* images, int batch, int layer, in
       fp::GemmParams p;
       p.M = M; p.N = D; p.K = D;
       p.bias = bw.proj_b; p.gamma = bw.ls1; p.out_f32 = h->x; p.ld_f32 = D;
-      if ((rc = fp::gemm_tn(fp::EPI_RESID_F32, h->attn, D, static_cast<const __half*>(bw.proj_w), D,
-                            p, stream)) != 0) return rc;
+      if (fused) {
+        p.x16 = h->xn; p.ld_x16 = D; p.stats_out = h->stats;
+      }
+      if ((rc = fp::gemm_tn(fused ? fp::EPI_RESID_LN_F32 : fp::EPI_RESID_F32, h->attn, D,
+                            static_cast<const __half*>(bw.proj_w), D, p, stream)) != 0) return rc;
     }
     // x = x + ls2 * fc2(gelu(fc1(norm2(x))))
-    if ((rc = fp::layernorm_f16(h->x, h->xn, bw.norm2_w, bw.norm2_b, M, D, eps, stream)) != 0) return rc;
+    if (!fused) {
+      if ((rc = fp::layernorm_f16(h->x, h->xn, bw.norm2_w, bw.norm2_b, M, D, eps, stream)) != 0) return rc;
+    }
     {
       fp::GemmParams p;
       p.M = M; p.N = 4 * D; p.K = D;
       p.bias = bw.fc1_b; p.out_f16 = h->hidden; p.ld_f16 = 4 * D;
-      if ((rc = fp::gemm_tn(fp::EPI_BIAS_GELU_F16, h->xn, D, static_cast<const __half*>(bw.fc1_w), D,
-                            p, stream)) != 0) return rc;
+      if (fused) {
+        p.ln_stats = h->stats; p.ln_slots = D / 128; p.ln_colsum = bw.fc1_colsum; p.ln_dim = D; p.ln_eps = eps;
+      }
+      if ((rc = fp::gemm_tn(fused ? fp::EPI_LN_BIAS_GELU_F16 : fp::EPI_BIAS_GELU_F16, h->xn, D,
+                            static_cast<const __half*>(bw.fc1_w), D, p, stream)) != 0) return rc;
     }
     {
       fp::GemmParams p;
       p.M = M; p.N = D; p.K = 4 * D;
       p.bias = bw.fc2_b; p.gamma = bw.ls2; p.out_f32 = h->x; p.ld_f32 = D;
-      if ((rc = fp::gemm_tn(fp::EPI_RESID_F32, h->hidden, 4 * D,
+      const bool last = i == layer;   // nothing reads the fp16 copy / sums of the last block's output
+      if (fused && !last) {
+        p.x16 = h->xn; p.ld_x16 = D; p.stats_out = h->stats;
+      }
+      if ((rc = fp::gemm_tn((fused && !last) ? fp::EPI_RESID_LN_F32 : fp::EPI_RESID_F32, h->hidden, 4 * D,
                             static_cast<const __half*>(bw.fc2_w), 4 * D, p, stream)) != 0) return rc;
     }
   }

@@ -52,6 +52,31 @@ __global__ void patchify_normalize_kernel(const float* __restrict__ img, __half*
   }
 }
 
+// LayerNorm-fused mode: the cls / register rows also need their fp16 copy and (sum x, sum x^2): one warp per row,
+// the full-row sums go to slot 0, the other slots are zero.
+__global__ void special_tokens_ln_kernel(const float* __restrict__ x, __half* __restrict__ x16,
+                                         float* __restrict__ stats, int B, int ntok, int R, int D, int slots) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int total = B * (1 + R);
+  for (int o = blockIdx.x * wpb + (threadIdx.x >> 5); o < total; o += gridDim.x * wpb) {
+    const long row = static_cast<long>(o / (1 + R)) * ntok + (o % (1 + R));
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float v = x[row * D + i];
+      x16[row * D + i] = __float2half_rn(v);
+      s1 += v;
+      s2 = fmaf(v, v, s2);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    for (int t = lane; t < slots; t += 32) {
+      stats[(row * slots + t) * 2] = t == 0 ? s1 : 0.f;
+      stats[(row * slots + t) * 2 + 1] = t == 0 ? s2 : 0.f;
+    }
+  }
+}
+
 // x[b, 0, :] = cls_pos ; x[b, 1..R, :] = reg[r]
 __global__ void init_special_tokens_kernel(float* __restrict__ x, const float* __restrict__ cls_pos,
                                            const float* __restrict__ reg, int B, int ntok, int R,
@@ -202,11 +227,19 @@ int patchify_normalize(const float* img, __half* out, int B, int H, int W, int p
 }
 
 int init_special_tokens(float* x, const float* cls_pos, const float* reg, int B, int ntok, int R,
-                        int D, cudaStream_t stream) {
+                        int D, cudaStream_t stream, __half* x16, float* stats, int stat_slots) {
   const long total = static_cast<long>(B) * (1 + R) * D;
-  ProfScope prof(PROF_VIT_MISC, stream, static_cast<double>(total) * 4);
-  init_special_tokens_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, cls_pos, reg, B, ntok, R, D);
-  FP_CUDA_CHECK(cudaGetLastError());
+  {
+    ProfScope prof(PROF_VIT_MISC, stream, static_cast<double>(total) * 4);
+    init_special_tokens_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, cls_pos, reg, B, ntok, R, D);
+    FP_CUDA_CHECK(cudaGetLastError());
+  }
+  if (x16 != nullptr) {
+    ProfScope prof(PROF_VIT_MISC, stream, static_cast<double>(total) * 6);
+    special_tokens_ln_kernel<<<grid_for(static_cast<long>(B) * (1 + R), 8), 256, 0, stream>>>(
+        x, x16, stats, B, ntok, R, D, stat_slots);
+    FP_CUDA_CHECK(cudaGetLastError());
+  }
   return 0;
 }
 

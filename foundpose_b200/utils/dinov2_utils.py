@@ -237,29 +237,49 @@ class DinoFeatureExtractor(nn.Module):
         weights.pos_patch = f32(pos[1:]).data_ptr()
         weights.norm_w = f32(sd["norm.weight"]).data_ptr()
         weights.norm_b = f32(sd["norm.bias"]).data_ptr()
+        # LayerNorm fused into the GEMMs around it (csrc/kernels.h, EPI_LN_*): needs the pair GEMM kernel, i.e.
+        # D % 256 == 0 and more than 256 patch rows per call (always true at 420 x 420).
+        #   LN(x) W^T + b = rstd (x W'^T - mu colsum(W')) + b',  W' = W diag(gamma), b' = b + W beta
+        fuse_ln = (d % 256 == 0 and (h // ps) * (w // ps) > 256
+                   and os.environ.get("FOUNDPOSE_FUSE_LAYERNORM", "1") != "0")
+
+        def fold(weight: torch.Tensor, bias: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+            w64 = weight.double().cpu()
+            w16 = (w64 * gamma.double().cpu()[None, :]).to(torch.float32).to(torch.float16)
+            colsum = w16.double().sum(dim=1).to(torch.float32)       # of the fp16 values the GEMM multiplies
+            b_fold = (bias.double().cpu() + w64 @ beta.double().cpu()).to(torch.float32)
+            return f16(w16).data_ptr(), f32(b_fold).data_ptr(), f32(colsum).data_ptr()
+
         blocks = []
         for i in range(n_blocks):
             p = f"blocks.{i}."
             bw = _native.VitBlockWeights()
             bw.norm1_w = f32(sd[p + "norm1.weight"]).data_ptr()
             bw.norm1_b = f32(sd[p + "norm1.bias"]).data_ptr()
-            bw.qkv_w = f16(sd[p + "attn.qkv.weight"]).data_ptr()
-            bw.qkv_b = f32(sd[p + "attn.qkv.bias"]).data_ptr()
+            if fuse_ln:
+                bw.qkv_w, bw.qkv_b, bw.qkv_colsum = fold(sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"],
+                                                         sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+                bw.fc1_w, bw.fc1_b, bw.fc1_colsum = fold(sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"],
+                                                         sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+            else:
+                bw.qkv_w = f16(sd[p + "attn.qkv.weight"]).data_ptr()
+                bw.qkv_b = f32(sd[p + "attn.qkv.bias"]).data_ptr()
+                bw.fc1_w = f16(sd[p + "mlp.fc1.weight"]).data_ptr()
+                bw.fc1_b = f32(sd[p + "mlp.fc1.bias"]).data_ptr()
             bw.proj_w = f16(sd[p + "attn.proj.weight"]).data_ptr()
             bw.proj_b = f32(sd[p + "attn.proj.bias"]).data_ptr()
             bw.ls1 = f32(sd[p + "ls1.gamma"]).data_ptr()
             bw.norm2_w = f32(sd[p + "norm2.weight"]).data_ptr()
             bw.norm2_b = f32(sd[p + "norm2.bias"]).data_ptr()
-            bw.fc1_w = f16(sd[p + "mlp.fc1.weight"]).data_ptr()
-            bw.fc1_b = f32(sd[p + "mlp.fc1.bias"]).data_ptr()
             bw.fc2_w = f16(sd[p + "mlp.fc2.weight"]).data_ptr()
             bw.fc2_b = f32(sd[p + "mlp.fc2.bias"]).data_ptr()
             bw.ls2 = f32(sd[p + "ls2.gamma"]).data_ptr()
             blocks.append(bw)
-        cfg = _native.VitConfig(d, self.arch.num_heads, n_blocks, self.arch.num_register_tokens, ps, h, w)
+        cfg = _native.VitConfig(d, self.arch.num_heads, n_blocks, self.arch.num_register_tokens, ps, h, w,
+                                int(fuse_ln))
         with torch.cuda.device(device):
             handle = _native.vit_create(cfg, weights, blocks, self.max_batch)
-        entry = {"handle": handle, "keep": keep, "hp": h // ps, "wp": w // ps}
+        entry = {"handle": handle, "keep": keep, "hp": h // ps, "wp": w // ps, "fuse_ln": fuse_ln}
         self._native_cache[key] = entry
         return entry
 

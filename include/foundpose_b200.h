@@ -78,6 +78,9 @@ typedef struct {
   int num_register_tokens;  /* 0 or 4 */
   int patch_size;           /* 14 */
   int img_h, img_w;         /* multiples of patch_size */
+  int fuse_layernorm;       /* 1: norm1 / norm2 (layers/block.py:63,75) are folded into the GEMMs around them - the
+                               caller passes gamma-folded qkv_w / fc1_w, beta-folded qkv_b / fc1_b and the column
+                               sums below; needs embed_dim % 256 == 0.  0: separate LayerNorm kernels. */
 } fp_vit_config;
 
 typedef struct {            /* device pointers; the caller keeps them alive while the handle lives */
@@ -102,6 +105,10 @@ typedef struct {            /* one transformer block; weights f16 [out, in], vec
   const void* fc1_w; const float* fc1_b;     /* [4D, D], [4D] */
   const void* fc2_w; const float* fc2_b;     /* [D, 4D], [D]  */
   const float* ls2;
+  /* fuse_layernorm = 1 only.  With W' = f16(W diag(norm_w)) passed as qkv_w / fc1_w and b' = b + W norm_b passed
+   * as qkv_b / fc1_b:  LN(x) W^T + b = rstd (x W'^T - mu colsum) + b',  colsum[n] = sum_k W'[n,k] (fp32). */
+  const float* qkv_colsum;                   /* [3D] */
+  const float* fc1_colsum;                   /* [4D] */
 } fp_vit_block_weights;
 
 /* Allocates the activation workspace for up to max_batch images. */

@@ -175,3 +175,37 @@ def test_checkpoint_file_is_loaded_through_the_env_hook(tmp_path, monkeypatch):
     assert set(from_file.model.state_dict()) == set(direct.model.state_dict())
     images = synthetic.make_crops(1, (420, 420), seed=4).cuda()
     assert torch.equal(from_file(images)["feature_maps"], direct(images)["feature_maps"])
+
+
+@pytest.mark.parametrize("realistic", [False, True])
+def test_layernorm_fused_into_the_gemms_matches_the_separate_kernels(monkeypatch, realistic):
+    """ViT-L/14: norm1 / norm2 folded into the qkv / fc1 GEMMs (raw fp16 residual rows as the operand, (mu, rstd)
+    applied in the epilogue, statistics from the partial sums the proj / fc2 / patch-embed epilogues emit) against
+    the separate LayerNorm kernels and against the fp32 oracle - also with pretrained-like statistics, where the
+    raw rows carry outlier channels at 80-300."""
+    from foundpose_b200.utils import dinov2_utils
+    from oracle import vit as ovit
+
+    arch = synthetic.VIT_ARCHS["vitl14"]
+    make = synthetic.make_vit_state_dict_realistic if realistic else synthetic.make_vit_state_dict
+    sd = make(arch, seed=13, depth=10)
+    images = synthetic.make_crops(2, (420, 420), seed=14)
+    name = "dinov2_version=vitl14_stride=14_facet=token_layer=9_norm=1"
+    monkeypatch.setenv("FOUNDPOSE_FUSE_LAYERNORM", "1")
+    fused = dinov2_utils.DinoFeatureExtractor(name, state_dict=sd).to("cuda")
+    out_f = fused(images.cuda())
+    assert fused._native_cache[(420, 420, "cuda:0")]["fuse_ln"] is True
+    monkeypatch.setenv("FOUNDPOSE_FUSE_LAYERNORM", "0")
+    plain = dinov2_utils.DinoFeatureExtractor(name, state_dict=sd).to("cuda")
+    out_p = plain(images.cuda())
+    assert plain._native_cache[(420, 420, "cuda:0")]["fuse_ln"] is False
+    ref = ovit.extract(sd, arch, images, layer=9, num_blocks=10)
+    e_f = _rel(out_f["feature_maps"].cpu(), ref["feature_maps"])
+    e_p = _rel(out_p["feature_maps"].cpu(), ref["feature_maps"])
+    print(f"vitl14 realistic={realistic}: rel err fused {e_f:.2e}, separate {e_p:.2e}, fused vs separate "
+          f"{_rel(out_f['feature_maps'].cpu(), out_p['feature_maps'].cpu()):.2e}")
+    assert torch.isfinite(out_f["feature_maps"]).all()
+    assert e_f <= 1e-2 and e_p <= 1e-2
+    assert _rel(out_f["cls_tokens"].cpu(), ref["cls_tokens"]) <= 1e-2
+    # deterministic: the partial sums are combined in a fixed order (no atomics)
+    assert torch.equal(fused(images.cuda())["feature_maps"], out_f["feature_maps"])
