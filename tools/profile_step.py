@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
-"""Runs a few steps of the bench workload inside a cudaProfilerStart/Stop range (for ncu).
+"""Runs micro-batches of a bench workload inside a cudaProfilerStart/Stop range (for ncu).
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-        --log-file gpurun_out/launches.csv python tools/profile_step.py --steps 1
+        --log-file gpurun_out/launches.csv python tools/profile_step.py --micro 1
     ncu --profile-from-start off --set full --clock-control none --import-source on \
-        -k regex:gemm_tn_kernel -c 6 -o gpurun_out/prof_gemm python tools/profile_step.py --steps 1
+        -o gpurun_out/prof_step python tools/profile_step.py --micro 1
 
+One micro-batch = 64 crops through the whole path of the workload (config3: incl. the full-bank search K4).
 Numbers printed under ncu are never bench values; this script prints none.
 """
 import argparse
@@ -22,43 +23,41 @@ import bench  # noqa: E402
 
 def main() -> None:
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="config2")
-    ap.add_argument("--steps", type=int, default=1)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="config3")
+    ap.add_argument("--micro", type=int, default=1, help="micro-batches inside the profiled range")
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--no-k4", action="store_true")
     args = ap.parse_args()
     from foundpose_b200 import pipeline, synthetic
-    from foundpose_b200.utils import dinov2_utils, knn_util, projector_util, repre_util, template_util
+    from foundpose_b200.utils import dinov2_utils, knn_util
 
     dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
     wl = bench.WORKLOADS[args.workload]
     B = wl["batch"]
     arch, opts = bench.vit_arch_and_layer(wl["vit"])
     sd = synthetic.make_vit_state_dict(arch, seed=0, depth=opts["layer"] + 1)
     extractor = dinov2_utils.DinoFeatureExtractor(wl["vit"], state_dict=sd, max_batch=B).to(dev)
-    pdict = synthetic.make_pca(arch.embed_dim, wl["dim"], seed=0)
-    projectors = [projector_util.projector_from_tensordict(pdict)]
-    bank = bench.build_bank_cpu(wl)
-    feat, centroids = bank["feat_vectors"].to(dev), bank["feat_cluster_centroids"].to(dev)
-    tpl_ids = bank["feat_to_template_ids"].to(dev)
-    wk = knn_util.KNN(k=1, metric="l2")
-    wk.fit(centroids)
-    f2w = wk.search(feat)[1].flatten()
-    descs, idfs = template_util.calc_tfidf_descriptors(feat, f2w, tpl_ids, centroids, wl["templates"], 3, False, 10.0)
-    repre = repre_util.FeatureBasedObjectRepre(
-        vertices=bank["vertices"].to(dev), feat_vectors=feat, feat_to_template_ids=tpl_ids,
-        feat_cluster_centroids=centroids, feat_cluster_idfs=idfs, template_descs=descs,
-        template_desc_opts=repre_util.TemplateDescOpts(), feat_raw_projectors=projectors)
+    repre, bank, pdict, _ = bench.build_repre_on_device(wl, dev, 0, 1)
     index = pipeline.ObjectIndex(repre, dev)
-    pipe = pipeline.CropBatchPipeline(extractor, index, projectors, B, top_n_templates=wl["top_n"],
+    pipe = pipeline.CropBatchPipeline(extractor, index, repre.feat_raw_projectors, B, top_n_templates=wl["top_n"],
                                       top_k_buddies=wl["top_k"])
+    k4 = 0 if args.no_k4 else wl["k4"]
+    k4_index = knn_util.KNN.from_packed(index.bank16, index.bank_sqnorm, k=k4, metric="l2") if k4 else None
     images = [synthetic.make_crops(B, (420, 420), seed=100 + s).to(dev) for s in range(2)]
     masks = torch.ones(B, 420, 420, dtype=torch.uint8, device=dev)
-    for i in range(args.warmup):
+
+    def micro(i: int) -> None:
         pipe.run(images[i % 2], masks)
+        if k4_index is not None:
+            k4_index.search_packed(pipe.proj16, pipe.engine.q_sqnorm)
+
+    for i in range(args.warmup):
+        micro(i)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    for i in range(args.steps):
-        pipe.run(images[i % 2], masks)
+    for i in range(args.micro):
+        micro(i)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 
