@@ -176,6 +176,12 @@ def convert_rows_f16(x: torch.Tensor, l2_normalize: bool = False, out: Optional[
     return out
 
 
+def unit_rows_f16(x16: torch.Tensor, out: torch.Tensor, sqnorm: torch.Tensor) -> None:
+    """f16 rows -> unit f16 rows + their squared norms (fp_unit_rows_f16)."""
+    require_cuda(x16, "x16", torch.float16)
+    call("fp_unit_rows_f16", ptr(x16), ptr(out), ptr(sqnorm), _l(x16.shape[0]), _i(x16.shape[1]), stream_ptr(x16.device))
+
+
 def split_rows_f16(x: torch.Tensor, pattern: int, l2_normalize: bool, scale: float,
                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [rows, dim] -> f16 [rows, 3*dim] hi/lo split (fp_split_rows_f16)."""

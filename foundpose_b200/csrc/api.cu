@@ -188,6 +188,11 @@ int fp_row_sqnorm_f16(const void* x_f16, float* out, int64_t rows, int dim, void
                             static_cast<cudaStream_t>(stream));
 }
 
+int fp_unit_rows_f16(const void* x_f16, void* y_f16, float* sqnorm, int64_t rows, int dim, void* stream) {
+  return fp::unit_rows_f16(static_cast<const __half*>(x_f16), static_cast<__half*>(y_f16), sqnorm, rows, dim,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int fp_split_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int pattern, int l2_normalize,
                       float scale, void* stream) {
   return fp::split_rows_f16(x, static_cast<__half*>(y_f16), rows, dim, pattern, l2_normalize, scale,

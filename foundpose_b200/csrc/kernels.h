@@ -101,6 +101,7 @@ int knn_merge(const float* part_d, const int64_t* part_i, int num_chunks, int q_
 int row_sqnorm_f16(const __half* x, float* out, long rows, int dim, cudaStream_t stream);
 int convert_rows_f16(const float* x, __half* y, long rows, int dim, int l2_normalize,
                      cudaStream_t stream);
+int unit_rows_f16(const __half* x, __half* y, float* sqnorm, long rows, int dim, cudaStream_t stream);
 int split_rows_f16(const float* x, __half* y, long rows, int dim, int pattern, int l2_normalize, float scale,
                    cudaStream_t stream);
 int knn_search_items(const __half* q, long q_rows_total, const __half* x, long x_rows_total, int dim,

@@ -718,6 +718,39 @@ __global__ void convert_rows_kernel(const float* __restrict__ x, __half* __restr
   }
 }
 
+// fp16 rows -> L2-normalised fp16 rows + their ||.||^2 (fp32, of the ROUNDED unit rows) in one pass: the query side
+// of the cosine visual-word metric (utils/knn_util.py:93: faiss.normalize_L2 on the search vectors), fused so
+// that the projected descriptors are read once.  One warp per row.
+__global__ void unit_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y, float* __restrict__ sqn,
+                                 long rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long row = blockIdx.x * static_cast<long>(wpb) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long>(gridDim.x) * wpb) {
+    const __half2* p = reinterpret_cast<const __half2*>(x + row * dim);
+    float s = 0.f;
+    for (int i = lane; i < dim / 2; i += 32) {
+      const float2 f = __half22float2(p[i]);
+      s = fmaf(f.x, f.x, fmaf(f.y, f.y, s));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.0f / sqrtf(s);
+    __half2* q = reinterpret_cast<__half2*>(y + row * dim);
+    float t = 0.f;
+    for (int i = lane; i < dim / 2; i += 32) {
+      const float2 f = __half22float2(p[i]);
+      const __half2 h = __floats2half2_rn(f.x * inv, f.y * inv);
+      q[i] = h;
+      const float2 g = __half22float2(h);
+      t = fmaf(g.x, g.x, fmaf(g.y, g.y, t));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) sqn[row] = t;
+  }
+}
+
 // fp32 rows -> THREE fp16 column blocks whose pairwise products reproduce the fp32 inner product on the tensor
 // cores: x = hi + lo (hi = fp16(x), lo = fp16(x - hi): 22 significant bits), and
 //     <a, b> ~= <a_hi, b_hi> + <a_lo, b_hi> + <a_hi, b_lo>       (the lo.lo term is below fp32 resolution)
@@ -869,6 +902,17 @@ int convert_rows_f16(const float* x, __half* y, long rows, int dim, int l2_norma
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   ProfScope prof(PROF_FEATURE, stream, static_cast<double>(rows) * dim * 6);
   convert_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, rows, dim, l2_normalize);
+  FP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int unit_rows_f16(const __half* x, __half* y, float* sqnorm, long rows, int dim, cudaStream_t stream) {
+  if (rows == 0) return 0;
+  FP_REQUIRE(dim % 2 == 0, "unit_rows: dim must be even");
+  long blocks = (rows + 7) / 8;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  ProfScope prof(PROF_FEATURE, stream, static_cast<double>(rows) * dim * 4);
+  unit_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, sqnorm, rows, dim);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -242,13 +242,12 @@ class RetrievalEngine:
             _native.knn_search_items(feat16, self.q_sqnorm, ix.centroids16, ix.centroid_sqnorm, self.items_words,
                                      self.n_items_words, 0, self.knn_k, self.word_d, self.word_i)
         else:
-            # cosine: normalised copies of the queries, inner-product search, distance = 1 - similarity
-            # (knn_util.py:84-98).  Not the shipped configuration, so the copy is not fused.
+            # cosine: normalised copies of the queries (one fused pass over the projected descriptors), inner-product
+            # search, distance = 1 - similarity (knn_util.py:84-98).
             if self.q_unit16 is None:
                 self.q_unit16 = torch.empty_like(feat16)
                 self.q_unit_sqnorm = torch.empty_like(self.q_sqnorm)
-            _native.convert_rows_f16(feat16.float(), l2_normalize=True, out=self.q_unit16)
-            _native.row_sqnorm_f16(self.q_unit16, self.q_unit_sqnorm)
+            _native.unit_rows_f16(feat16, self.q_unit16, self.q_unit_sqnorm)
             _native.knn_search_items(self.q_unit16, self.q_unit_sqnorm, ix.centroids16, ix.centroid_sqnorm,
                                      self.items_words, self.n_items_words, 1, self.knn_k, self.word_d, self.word_i)
             torch.sub(1.0, self.word_d, out=self.word_d)

@@ -132,6 +132,10 @@ int fp_convert_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int 
 /* out[r] = ||x[r]||^2 (fp32) of f16 rows; the ||x||^2 term of faiss's L2 expansion. */
 int fp_row_sqnorm_f16(const void* x_f16, float* out, int64_t rows, int dim, void* stream);
 
+/* f16 rows -> L2-normalised f16 rows and their ||.||^2 (fp32) in one pass: the query side of the cosine metric
+ * (faiss.normalize_L2 at utils/knn_util.py:93) for descriptors that are already packed as f16. */
+int fp_unit_rows_f16(const void* x_f16, void* y_f16, float* sqnorm, int64_t rows, int dim, void* stream);
+
 /* fp32 rows [rows, dim] -> f16 rows [rows, 3*dim] holding the split x = hi + lo as [hi | lo | hi] (pattern 0, index
  * side) or [hi | hi | lo] (pattern 1, query side): one inner-product search over the 3*dim columns then evaluates
  * <a,b> to fp32 accuracy on the tensor cores.  Rows are optionally L2-normalised first (zero rows stay zero) and

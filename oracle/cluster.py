@@ -4,7 +4,21 @@ Reference call site: utils/cluster_util.py:13-68 - `faiss.Kmeans(d, k, niter=50,
 `.train(samples)`, then `kmeans.index.search(samples, 1)`; used by scripts/gen_repre.py:289-300 to turn
 the template features into 2048 visual words.  faiss 1.8.0 (conda_foundpose_gpu.yaml:19) is a third-party
 dependency absent from /root/reference and from this image - **parity unpinned against faiss binaries**.
-This file restates its published algorithm (faiss/Clustering.cpp, faiss/utils/random.cpp):
+This file restates its published algorithm.  Step -> faiss 1.8.0 function it follows (faiss is not available
+offline, so functions are named instead of line numbers that could not be verified here):
+
+  rand_perm                   faiss/utils/random.cpp  `rand_perm(int* perm, size_t n, int64_t seed)`
+  subsampling in `kmeans`     faiss/Clustering.cpp    `subsample_training_set` (called from `Clustering::train_encoded`
+                                                      when nx > k * max_points_per_centroid, seed = cp.seed)
+  initial centroids           faiss/Clustering.cpp    `Clustering::train_encoded`: `rand_perm(perm, nx, seed + 1 + redo)`,
+                                                      centroid i = sample perm[i]  (nredo = 1 -> redo = 0)
+  assign_nearest              faiss/Clustering.cpp    `index.search(nx, x, 1, dis, assign)` on an IndexFlatL2 holding
+                                                      the centroids (exhaustive_L2sqr_blas, see oracle/knn.py)
+  update_centroids            faiss/Clustering.cpp    `compute_centroids`: per-centroid sum of its samples / count
+  split_clusters              faiss/Clustering.cpp    `split_clusters`: RandomGenerator rng(1234), EPS = 1/1024
+  final assignment            faiss/Clustering.cpp    kmeans.index.search(samples, 1) at utils/cluster_util.py:54-56
+
+Algorithm:
 
   * more than k*256 samples: train on the first k*256 entries of `rand_perm(n, seed)`;
   * initial centroids: the first k entries of `rand_perm(nx, seed + 1)`;

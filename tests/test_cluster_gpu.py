@@ -80,3 +80,26 @@ def test_kmeans_subsampling_and_objective():
         cluster_util.kmeans(x[:5].cuda(), 16)
     with pytest.raises(ValueError):
         cluster_util.kmeans(x, 16)                     # CPU tensor: no fallback
+
+
+def test_kmeans_is_exact_against_the_oracle_when_every_assignment_has_a_margin():
+    """fp16-representable samples in well separated blobs, arranged so that faiss's initialisation (the first k
+    entries of rand_perm(n, seed + 1)) picks one sample per blob: every assignment of every iteration then has a
+    large margin, and the whole run must equal the oracle bit for bit - ids, centroids (fixed-point update) - with
+    distances within 1e-3 relative."""
+    from foundpose_b200.utils import cluster_util
+    from oracle import cluster as ocluster
+
+    k, n, d = 12, 3000, 64
+    g = torch.Generator().manual_seed(5)
+    centers = (torch.randn(k, d, generator=g) * 8).half().float()
+    blob = torch.randint(0, k, (n,), generator=g)
+    init = ocluster.rand_perm(n, 0 + 1)[:k]                   # n <= k * 256: no sub-sampling, seed 0
+    blob[torch.from_numpy(init)] = torch.arange(k)            # one initial centroid per blob
+    x = (centers[blob] + 0.25 * torch.randn(n, d, generator=g)).half().float()
+    cent, ids, dist = cluster_util.kmeans(x.cuda(), k, num_iter=6, verbose=False)
+    rc, ri, rd, _ = ocluster.kmeans(x, k, num_iter=6)
+    assert torch.equal(ri.to(torch.int64), blob)              # the clustering is the blob structure
+    assert torch.equal(ids.cpu(), ri)                         # bit-exact assignments
+    assert np.array_equal(cent.cpu().numpy(), rc.numpy())     # bit-exact centroids
+    assert torch.allclose(dist.cpu(), rd, rtol=1e-3, atol=1e-4)
