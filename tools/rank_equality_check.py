@@ -48,8 +48,15 @@ def main() -> int:
         outs = {f: [] for f in fields}
         for s in range(lo, hi, B):
             out = pipe.run(images[s:s + B].to(dev), masks[s:s + B].to(dev))
+            # rows at and beyond count[b, j] of the [B, topn, K, ...] buffers are not part of the result (they keep
+            # whatever an earlier batch left there): blank them so that only results are compared
+            k = out.query_ids.shape[2]
+            valid = torch.arange(k, device=dev).view(1, 1, k) < out.count.unsqueeze(-1)
             for f in fields:
-                outs[f].append(getattr(out, f).clone())
+                t = getattr(out, f).clone()
+                if t.dim() >= 3 and t.shape[2] == k:
+                    t = torch.where(valid if t.dim() == 3 else valid.unsqueeze(-1), t, torch.zeros_like(t))
+                outs[f].append(t)
         return {f: torch.cat(v) for f, v in outs.items()}
 
     lo, hi = distributed.shard_range(n_total, rank, world)
