@@ -837,6 +837,7 @@ def main() -> None:
     if args.workload in ("config4", "config5") and args.impl == "cuda":
         import bench_configs
 
+        bench_configs.bench = sys.modules[__name__]    # this module runs as __main__: share ITS stdout capture
         getattr(bench_configs, "run_" + args.workload)(args)
     elif args.impl == "reference":
         if args.workload == "config5":

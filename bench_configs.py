@@ -14,6 +14,7 @@
 from __future__ import annotations
 
 import ctypes
+import gc
 import os
 import time
 
@@ -270,6 +271,7 @@ def run_config5(args) -> None:
                 row["cpu_sample_rows"] = sample
             rows_out.append(row)
             del index, bank
+            gc.collect()                 # KNN.index refers to itself: the bank is only released by the collector
             torch.cuda.empty_cache()
     clocks = sampler.stop()
     gpu_launches = int(lib.fp_launch_count() - launches0)

@@ -611,7 +611,7 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * BX + half * (BX / 2) + c * 32, v);
             tmem_ld_wait();
-            if (__uint_as_float(v[lane]) == 1.2345e30f) best.d[0] = 0.f;   // keep the load alive
+            if (__uint_as_float(v[0]) + __uint_as_float(v[31]) == 1.2345e30f) best.d[0] = 0.f;   // keep the load alive
           }
         } else if (!(L.flags & 1))
           scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,

@@ -102,4 +102,6 @@ def test_kmeans_is_exact_against_the_oracle_when_every_assignment_has_a_margin()
     assert torch.equal(ri.to(torch.int64), blob)              # the clustering is the blob structure
     assert torch.equal(ids.cpu(), ri)                         # bit-exact assignments
     assert np.array_equal(cent.cpu().numpy(), rc.numpy())     # bit-exact centroids
-    assert torch.allclose(dist.cpu(), rd, rtol=1e-3, atol=1e-4)
+    # ||x||^2 ~ 4000 against distances ~ 2-5: the expansion ||q||^2 + ||x||^2 - 2<q,x> (faiss's too) cancels to ~1e-3
+    # absolute in fp32, whatever the accumulation order
+    assert torch.allclose(dist.cpu(), rd, rtol=1e-3, atol=4e-3)
