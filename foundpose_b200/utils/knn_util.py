@@ -145,6 +145,10 @@ class KNN:
             q16 = _native.convert_rows_f16(q, l2_normalize=cosine)
             qn = _native.row_sqnorm_f16(q16)
             dist, idx = self.search_packed(q16, qn, dist, idx)
+            if dist._base is not None:
+                # the pair path returns views of buffers it reuses for the next search of the same shape:
+                # the public API hands out tensors the caller owns
+                dist, idx = dist.clone(), idx.clone()
             if cosine:
                 dist = 1.0 - dist  # cosine similarity -> cosine distance (reference :98)
         return dist.to(out_device), idx.to(out_device)
@@ -153,7 +157,9 @@ class KNN:
                       idx: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """Search with already packed fp16 query rows (and their fp32 ||q||^2): no conversion, no host sync.
 
-        Returns raw kernel outputs (squared L2 ascending, or inner products descending for metric "cosine").
+        Returns raw kernel outputs (squared L2 ascending, or inner products descending for metric "cosine").  On
+        the pair path the returned tensors are views of buffers that the NEXT search of the same shape overwrites
+        (no allocation in a steady-state loop): consume or copy them before searching again.
         Picks the pass structure from the problem shape: the pair kernel when the search is tensor-bound (>= 74
         query blocks x a large bank), bank slices over all SMs when it is HBM-bound (few query blocks x a large
         bank), one item per query block otherwise."""

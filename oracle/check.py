@@ -9,8 +9,10 @@ path saw them (chained inputs), and the end-to-end agreement through the fp16 Vi
                                                  descriptors within a relative Frobenius tolerance
   stage 2  tf-idf template retrieval            (utils/template_util.py:126-176) oracle on the CUDA path's own
            descriptors (fp16 rows, read back)    -> template ids bit-exact where the score gap allows
-  stage 3  cyclic buddies per retrieved template (utils/corresp_util.py:34-70, 135-155) oracle on the CUDA
-           path's descriptors and ITS template ids -> 2D / 3D ids bit-exact where every 1-NN margin allows
+  stage 3  cyclic buddies per retrieved template (utils/corresp_util.py:34-70, 135-155), for the CUDA path's OWN
+           template ids: (a) the two 1-NN searches vs the oracle on the same descriptors -> ids equal wherever the
+           oracle's fp64 margin allows (asserted per query), distances within 1e-3; (b) cycle distances, top-k and
+           gathers vs the oracle on the CUDA path's own 1-NN ids -> 2D ids, 3D ids, distances bit-exact (asserted)
   stage 4  full-bank k-NN (benchmark search K4)  (utils/knn_util.py:65-106 over all feat_vectors) for a few
            queries, bank streamed block-wise from HBM -> ids bit-exact outside the tie margin, d within 1e-3
 
