@@ -236,25 +236,29 @@ def knn_search_items(q16, q_sqnorm, bank16, bank_sqnorm, items, num_items, metri
          stream_ptr(q16.device))
 
 
-def knn_search_pair_items(q16, q_sqnorm, bank16, bank_sqnorm, items, num_items, metric: int, k: int, out_d, out_i) -> None:
-    """Pair kernel (cta_group::2, queries resident in shared memory); items hold up to 256 query rows."""
+def knn_search_pair_items(q16, q_sqnorm, bank16, bank_sqnorm, items, num_items, metric: int, k: int, out_d, out_i,
+                          sync_counter: Optional[torch.Tensor] = None, sync_tiles: int = 0) -> None:
+    """Pair kernel (cta_group::2, queries resident in shared memory); items hold up to 256 query rows.
+    sync_counter (int64 [1], device) + sync_tiles > 0 enable the sweep barrier of items whose 4th word is set."""
     require_cuda(q16, "q16", torch.float16)
     require_cuda(bank16, "bank16", torch.float16)
     assert q16.shape[1] == bank16.shape[1]
     call("fp_knn_search_pair_items", ptr(q16), _l(q16.shape[0]), ptr(q_sqnorm), ptr(bank16), _l(bank16.shape[0]),
          ptr(bank_sqnorm), _i(q16.shape[1]), ptr(items), _i(num_items), _i(metric), _i(k), ptr(out_d), ptr(out_i),
-         stream_ptr(q16.device))
+         ptr(sync_counter), _i(sync_tiles if sync_counter is not None else 0), stream_ptr(q16.device))
 
 
 def knn_items_from_host(rows, device) -> torch.Tensor:
-    """Device fp_knn_item array from host tuples (q_row0, q_rows, b_row0, b_rows, out_row0)."""
+    """Device fp_knn_item array from host tuples (q_row0, q_rows, b_row0, b_rows, out_row0[, sweep participants])."""
     import numpy as np
 
     arr = np.zeros((max(len(rows), 1), 4), dtype=np.int64)
-    for n, (q0, qr, b0, br, o0) in enumerate(rows):
+    for n, row in enumerate(rows):
+        q0, qr, b0, br, o0 = row[:5]
         arr[n, 0] = (int(q0) & 0xFFFFFFFF) | (int(qr) << 32)
         arr[n, 1] = (int(b0) & 0xFFFFFFFF) | (int(br) << 32)
         arr[n, 2] = int(o0)
+        arr[n, 3] = int(row[5]) if len(row) > 5 else 0
     return torch.from_numpy(arr).to(device)
 
 

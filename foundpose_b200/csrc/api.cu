@@ -202,6 +202,10 @@ int fp_split_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int pa
 int fp_pca_project(const void* x_f16, const void* components_f16, const float* bias, int M, int D,
                    int d, float* out_f32, void* out_f16, void* stream) {
   if (M <= 0) return 0;
+  if (out_f32 == nullptr && out_f16 == nullptr) {
+    fp::set_last_error("fp_pca_project: out_f32 and out_f16 are both NULL");
+    return 1;
+  }
   fp::GemmParams p;
   p.M = M; p.N = d; p.K = D;
   p.bias = bias;
@@ -249,7 +253,7 @@ int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_
 int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const float* q_sqnorm,
                              const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
                              int dim, const fp_knn_item* items, int num_items, int metric, int k,
-                             float* out_d, int64_t* out_i, void* stream) {
+                             float* out_d, int64_t* out_i, uint64_t* sync_counter, int sync_tiles, void* stream) {
   if (metric != 0 && metric != 1) {
     fp::set_last_error("Metric %d is not supported.", metric);
     return 1;
@@ -258,6 +262,7 @@ int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const floa
                                    static_cast<const __half*>(bank_f16), bank_rows_total, dim,
                                    reinterpret_cast<const fp::KnnItem*>(items), num_items, q_sqnorm,
                                    bank_sqnorm, metric, k, out_d, out_i,
+                                   reinterpret_cast<unsigned long long*>(sync_counter), sync_tiles,
                                    static_cast<cudaStream_t>(stream));
 }
 

@@ -164,8 +164,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, int row, i
       v[j * 4 + 1] = __uint_as_float(r[j * 4 + 1]) + b.y;
       v[j * 4 + 2] = __uint_as_float(r[j * 4 + 2]) + b.z;
       v[j * 4 + 3] = __uint_as_float(r[j * 4 + 3]) + b.w;
-      *reinterpret_cast<float4*>(dst + j * 4) =
-          make_float4(v[j * 4 + 0], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+      if (p.out_f32 != nullptr)   // the fp32 copy is optional (the k-NN stages read the fp16 one)
+        *reinterpret_cast<float4*>(dst + j * 4) =
+            make_float4(v[j * 4 + 0], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
     }
     if (p.out_f16 != nullptr) {
       __half* d16 = p.out_f16 + static_cast<size_t>(row) * p.ld_f16 + n0;

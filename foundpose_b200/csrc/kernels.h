@@ -90,7 +90,7 @@ struct KnnItem {
   int b_row0;
   int b_rows;
   long long out_row0;
-  long long pad;
+  long long pad;   // pair kernel: number of clusters whose items sweep the same bank rows in lockstep (0 = none)
 };
 int knn_items_per_rows(int rows);
 int knn_build_items_dense(KnnItem* items, int q_total, int b_row0, int b_rows, cudaStream_t stream);
@@ -112,7 +112,8 @@ int knn_search_items(const __half* q, long q_rows_total, const __half* x, long x
 // Pair kernel (cta_group::2, queries resident in shared memory): items hold up to 256 query rows.
 int knn_search_pair_items(const __half* q, long q_rows_total, const __half* x, long x_rows_total, int dim,
                           const KnnItem* items, int num_items, const float* qnorm, const float* xnorm,
-                          int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream);
+                          int metric_ip, int k, float* out_d, int64_t* out_i, unsigned long long* sync_counter,
+                          int sync_tiles, cudaStream_t stream);
 
 
 void knn_set_flags(int flags);   // experiment switches of the pair kernel, 0 in production

@@ -466,7 +466,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kKnnThreads, 1)
 knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
                 const KnnItem* __restrict__ items, int num_items, int dim,
                 const float* __restrict__ qnorm, const float* __restrict__ xnorm, int metric_ip,
-                int k_out, float* __restrict__ out_d, int64_t* __restrict__ out_i, const PairLayout L) {
+                int k_out, float* __restrict__ out_d, int64_t* __restrict__ out_i, const PairLayout L,
+                unsigned long long* __restrict__ sync_counter, int sync_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -517,6 +518,7 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, qphase = 0;
+      unsigned long long sync_expected = 0;
       for (int it = cluster_id; it < num_items; it += num_clusters) {
         const KnnItem item = items[it];
         if (item.q_rows <= 0 || item.b_rows <= 0) continue;
@@ -528,7 +530,28 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           qphase ^= 1;
         }
         const int num_tiles = (item.b_rows + BX - 1) / BX;
+        // Items of one wave sweep the same bank rows: every `sync_tiles` tiles the leaders' producers of the
+        // `item.pad` participating clusters meet at a grid barrier (a monotonic counter in global memory), so that
+        // the 74 sweeps stay within a few MB of each other and the bank is read from HBM once per wave instead of
+        // once per cluster (ncu: 790 GB of DRAM reads per 57 600-query launch without it, L2 hit rate 57%).
+        const unsigned long long participants = static_cast<unsigned long long>(item.pad);
         for (int t = 0; t < num_tiles; ++t) {
+          if (sync_tiles > 0 && participants > 0 && rank == 0 && (t % sync_tiles) == 0) {
+            sync_expected += participants;
+            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(sync_counter) : "memory");
+            unsigned long long seen = 0;
+            uint32_t polls = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(sync_counter) : "memory");
+              if (seen >= sync_expected) break;
+              __nanosleep(64);
+              if (++polls > (1u << 26)) {
+                printf("foundpose_b200: k-NN sweep barrier timed out (block %d: %llu of %llu)\n", blockIdx.x, seen,
+                       sync_expected);
+                __trap();
+              }
+            } while (true);
+          }
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sx = stages + stage * L.stage_bytes;
@@ -648,12 +671,14 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   bit 0  epilogue warps skip the scan (main-loop speed alone; results are garbage)
 //   bit 1  stream the queries with the bank even when they would fit in shared memory
 //   bit 2  epilogue warps only read the accumulators out of TMEM (no arithmetic)
+//   bit 3  no sweep barrier: the clusters' bank sweeps run free
 int g_knn_flags = 0;
 
 template <int K>
 int launch_knn_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* items, int num_items,
                     int dim, const float* qnorm, const float* xnorm, int metric_ip, int k_out,
-                    float* out_d, int64_t* out_i, cudaStream_t stream) {
+                    float* out_d, int64_t* out_i, unsigned long long* sync_counter, int sync_tiles,
+                    cudaStream_t stream) {
   PairLayout L = pair_layout(dim);
   if ((g_knn_flags & 2) && L.q_resident) {
     L.q_resident = 0;
@@ -670,9 +695,11 @@ int launch_knn_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnIte
   }
   const int max_clusters = num_sms() / 2;
   const int clusters = num_items < max_clusters ? num_items : max_clusters;
+  if (sync_counter == nullptr || (g_knn_flags & 8)) sync_tiles = 0;   // bit 3: experiment, sweeps run free
+  if (sync_tiles > 0) FP_CUDA_CHECK(cudaMemsetAsync(sync_counter, 0, sizeof(unsigned long long), stream));
   ProfScope prof(PROF_KNN_PAIR, stream, 0.0);
   knn_pair_kernel<K><<<2 * clusters, kKnnThreads, L.smem_bytes, stream>>>(
-      tmQ, tmX, items, num_items, dim, qnorm, xnorm, metric_ip, k_out, out_d, out_i, L);
+      tmQ, tmX, items, num_items, dim, qnorm, xnorm, metric_ip, k_out, out_d, out_i, L, sync_counter, sync_tiles);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -819,17 +846,23 @@ __global__ void build_items_split_kernel(KnnItem* items, int q_blocks, int num_c
 }
 
 // Merge per-chunk top-k lists: part_* [num_chunks, q_pad, k] (indices relative to the chunk) ->
-// out_* [nq, k], ordered by (distance, global index).  One thread per query.
+// out_* [nq, k], ordered by (distance, global index).  One WARP per query: every lane folds the lists of chunks
+// lane, lane + 32, ... into its own sorted top-K, then k rounds of a warp-wide lexicographic argmin pop the global
+// winners (a single thread per query walking num_chunks * k candidates through a 16-deep insert took 175 us for the
+// 64 x 40 x 5 lists of the template scoring, ncu profiles/r02_ncu_retrieval.md).
 template <int K>
-__global__ void knn_merge_kernel(const float* __restrict__ part_d, const int64_t* __restrict__ part_i,
-                                 int num_chunks, int q_pad, int nq, int k, int chunk_rows, int b_rows,
-                                 int descending, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+knn_merge_kernel(const float* __restrict__ part_d, const int64_t* __restrict__ part_i,
+                 int num_chunks, int q_pad, int nq, int k, int chunk_rows, int b_rows,
+                 int descending, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
   TopK<K> best;
-  best.init();
-  for (int c = 0; c < num_chunks; ++c) {
-    if (c * chunk_rows >= b_rows) break;
+#pragma unroll
+  for (int j = 0; j < K; ++j) { best.d[j] = INFINITY; best.i[j] = 0x7fffffff; }
+  for (int c = lane; c < num_chunks; c += 32) {
+    if (static_cast<long>(c) * chunk_rows >= b_rows) break;
     const long base = (static_cast<long>(c) * q_pad + q) * k;
     for (int j = 0; j < k; ++j) {
       const long li = part_i[base + j];
@@ -838,10 +871,26 @@ __global__ void knn_merge_kernel(const float* __restrict__ part_d, const int64_t
       best.push_lex(descending ? -d : d, static_cast<int>(c * chunk_rows + li));
     }
   }
-  for (int j = 0; j < k; ++j) {
-    const bool ok = best.i[j] >= 0;
-    out_d[static_cast<long>(q) * k + j] = ok ? (descending ? -best.d[j] : best.d[j]) : (descending ? -INFINITY : INFINITY);
-    out_i[static_cast<long>(q) * k + j] = best.i[j];
+  for (int r = 0; r < k; ++r) {
+    float wd = best.d[0];
+    int wi = best.i[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, wd, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (od < wd || (od == wd && oi < wi)) { wd = od; wi = oi; }
+    }
+    if (best.i[0] == wi && wi != 0x7fffffff) {   // this lane held the winner: pop it
+#pragma unroll
+      for (int j = 0; j + 1 < K; ++j) { best.d[j] = best.d[j + 1]; best.i[j] = best.i[j + 1]; }
+      best.d[K - 1] = INFINITY;
+      best.i[K - 1] = 0x7fffffff;
+    }
+    if (lane == 0) {
+      const bool ok = wi != 0x7fffffff;
+      out_d[static_cast<long>(q) * k + r] = ok ? (descending ? -wd : wd) : (descending ? -INFINITY : INFINITY);
+      out_i[static_cast<long>(q) * k + r] = ok ? wi : -1;
+    }
   }
 }
 
@@ -869,8 +918,16 @@ int knn_merge(const float* part_d, const int64_t* part_i, int num_chunks, int q_
   FP_REQUIRE(k >= 1 && k <= 16, "knn_merge: k=%d is outside [1,16]", k);
   if (nq <= 0) return 0;
   ProfScope prof(PROF_RETRIEVAL, stream, static_cast<double>(num_chunks) * nq * k * 12);
-  knn_merge_kernel<16><<<(nq + 127) / 128, 128, 0, stream>>>(part_d, part_i, num_chunks, q_pad, nq, k, chunk_rows,
-                                                             b_rows, descending, out_d, out_i);
+  const int blocks = (nq + 7) / 8;   // 8 warps = 8 queries per block
+#define FP_MERGE_CASE(KK)                                                                                   \
+  knn_merge_kernel<KK><<<blocks, 256, 0, stream>>>(part_d, part_i, num_chunks, q_pad, nq, k, chunk_rows, b_rows, \
+                                                   descending, out_d, out_i)
+  if (k == 1) FP_MERGE_CASE(1);
+  else if (k <= 3) FP_MERGE_CASE(3);
+  else if (k <= 5) FP_MERGE_CASE(5);
+  else if (k <= 8) FP_MERGE_CASE(8);
+  else FP_MERGE_CASE(16);
+#undef FP_MERGE_CASE
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -954,7 +1011,8 @@ int knn_search_items(const __half* q, long q_rows_total, const __half* x, long x
 
 int knn_search_pair_items(const __half* q, long q_rows_total, const __half* x, long x_rows_total, int dim,
                           const KnnItem* items, int num_items, const float* qnorm, const float* xnorm,
-                          int metric_ip, int k, float* out_d, int64_t* out_i, cudaStream_t stream) {
+                          int metric_ip, int k, float* out_d, int64_t* out_i, unsigned long long* sync_counter,
+                          int sync_tiles, cudaStream_t stream) {
   FP_REQUIRE(k >= 1 && k <= 16, "knn: k=%d is outside the supported range [1,16]", k);
   FP_REQUIRE(dim % BKK == 0 && dim >= BKK, "knn: dim=%d must be a positive multiple of %d", dim, BKK);
   if (num_items <= 0 || q_rows_total <= 0) return 0;
@@ -964,7 +1022,7 @@ int knn_search_pair_items(const __half* q, long q_rows_total, const __half* x, l
   if (make_tma_2d_f16(&tmX, x, x_rows_total, dim, dim, 128) != 0) return 3;
 #define FP_KNN_CASE(KK)                                                                               \
   return launch_knn_pair<KK>(tmQ, tmX, items, num_items, dim, qnorm, xnorm, metric_ip, k, out_d, out_i, \
-                             stream)
+                             sync_counter, sync_tiles, stream)
   if (k == 1) FP_KNN_CASE(1);
   if (k <= 3) FP_KNN_CASE(3);
   if (k <= 5) FP_KNN_CASE(5);

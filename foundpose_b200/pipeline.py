@@ -275,7 +275,9 @@ class CropBatchPipeline:
 
     def __init__(self, extractor: Any, index: ObjectIndex, projectors: Optional[List[Any]], batch: int,
                  crop_size: Tuple[int, int] = (420, 420), grid_cell_size: float = 14.0,
-                 top_n_templates: int = 5, top_k_buddies: int = 300) -> None:
+                 top_n_templates: int = 5, top_k_buddies: int = 300, keep_f32_descriptors: bool = False) -> None:
+        """keep_f32_descriptors: also write the projected descriptors in fp32 (`proj32`, 88 MB per 64 crops at
+        d = 384); the matching stages only read the fp16 copy."""
         from foundpose_b200.utils import feature_util
 
         self.extractor = extractor
@@ -301,7 +303,7 @@ class CropBatchPipeline:
         self.sampled16 = torch.zeros((rows, d_vit), dtype=f16, device=dev)
         if self.projector is not None:
             d_out = self.projector["components16"].shape[0]
-            self.proj32 = torch.empty((rows, d_out), dtype=f32, device=dev)
+            self.proj32 = torch.empty((rows, d_out), dtype=f32, device=dev) if keep_f32_descriptors else None
             self.proj16 = torch.empty((rows, d_out), dtype=f16, device=dev)
             assert d_out == index.dim_padded, (d_out, index.dim_padded)
         else:

@@ -21,6 +21,9 @@ _SPLIT_BELOW_ITEMS = 74     # fewer query blocks than half the SMs -> split the 
 _SPLIT_MIN_ROWS = 16384
 _PAIR_ROWS = 256            # query rows per item of the pair kernel (fp_knn_search_pair_items)
 _PAIR_MIN_BANK_ROWS = 8192  # below this the per-item pipeline fill dominates: keep the 1-CTA kernel
+# bank tiles (256 rows) between two sweep barriers of the pair kernel: 64 tiles = 12.6 MB of a 384-d bank, a small
+# fraction of the L2, ~180 us of work per barrier
+_SWEEP_SYNC_TILES = int(os.environ.get("FOUNDPOSE_KNN_SWEEP_SYNC_TILES", "64"))
 _sm_count = [0]
 
 
@@ -201,21 +204,26 @@ class KNN:
         key = (nq, nb, self.k, str(dev))
         plan = getattr(self, "_pair_plan", None)
         if plan is None or plan[0] != key:
-            direct, split, chunks, chunk_rows = plan_pair_items(nq, nb, _num_sms() // 2)
+            clusters = _num_sms() // 2
+            direct, split, chunks, chunk_rows = plan_pair_items(nq, nb, clusters)
+            # items i, i + C, ... run on cluster i % C: the items of one wave sweep the whole bank together and meet
+            # at the kernel's sweep barrier (6th field = participants of the wave)
+            direct = [it + (min(clusters, len(direct) - (i // clusters) * clusters),) for i, it in enumerate(direct)]
             split = [(q0, qr, b0, br, o0 + nq) for (q0, qr, b0, br, o0) in split]   # partials live behind row nq
             rem = len(split) // chunks if split else 0
             rows = nq + chunks * rem * _PAIR_ROWS if split else nq
             plan = (key, _native.knn_items_from_host(direct + split, dev), len(direct), len(split), chunks, chunk_rows,
                     torch.empty((rows, self.k), dtype=torch.float32, device=dev),
-                    torch.empty((rows, self.k), dtype=torch.int64, device=dev))
+                    torch.empty((rows, self.k), dtype=torch.int64, device=dev),
+                    torch.zeros(1, dtype=torch.int64, device=dev))
             self._pair_plan = plan
-        _, items, n_direct, n_split, chunks, chunk_rows, buf_d, buf_i = plan
+        _, items, n_direct, n_split, chunks, chunk_rows, buf_d, buf_i, sync = plan
         if n_split == 0:
             _native.knn_search_pair_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_direct, metric, self.k,
-                                          dist, idx)
+                                          dist, idx, sync, _SWEEP_SYNC_TILES)
             return dist, idx
         _native.knn_search_pair_items(q16, qn, self._bank16, self._bank_sqnorm, items, n_direct + n_split, metric,
-                                      self.k, buf_d, buf_i)
+                                      self.k, buf_d, buf_i, sync, _SWEEP_SYNC_TILES)
         q_pad = (n_split // chunks) * _PAIR_ROWS
         first_tail = n_direct * _PAIR_ROWS
         _native.knn_merge(buf_d[nq:], buf_i[nq:], chunks, q_pad, nq - first_tail, self.k, chunk_rows, nb, metric == 1,

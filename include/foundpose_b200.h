@@ -148,8 +148,8 @@ int fp_split_rows_f16(const float* x, void* y_f16, int64_t rows, int dim, int pa
 /* ---- PCA projection ------------------------------------------------------------------------
  * out = x . components^T + bias, bias = -(mean . components^T)  (sklearn PCA.transform with
  * whiten=False as called at utils/projector_util.py:66-69).  x f16 [M,D], components f16 [d,D],
- * d % 128 == 0, D % 64 == 0.  Writes fp32 [M,d] and, if out_f16 != NULL, an f16 copy (the k-NN
- * operand). */
+ * d % 128 == 0, D % 64 == 0.  Writes fp32 [M,d] (if out_f32 != NULL) and an f16 copy (if out_f16 != NULL, the
+ * k-NN operand); at least one of the two. */
 int fp_pca_project(const void* x_f16, const void* components_f16, const float* bias, int M, int D,
                    int d, float* out_f32, void* out_f16, void* stream);
 
@@ -161,7 +161,7 @@ typedef struct {
   int32_t q_row0, q_rows;   /* query rows [q_row0, q_row0 + q_rows), q_rows <= 128 (0 = skip) */
   int32_t b_row0, b_rows;   /* bank rows  [b_row0, b_row0 + b_rows) */
   int64_t out_row0;         /* results go to output rows [out_row0, out_row0 + q_rows) */
-  int64_t reserved;
+  int64_t reserved;         /* fp_knn_search_pair_items: sweep-barrier participants of this item (see there); else 0 */
 } fp_knn_item;
 
 /* Number of items that cover q_rows query rows of one dense problem. */
@@ -189,11 +189,16 @@ int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_
  * BASELINE.json configs 3 and 5, queries of all crops vs the WHOLE bank; utils/knn_util.py:65-106 with
  * the full feat_vectors as the index).  Items hold up to 256 query rows (q_rows <= 256): a cluster of
  * two CTAs keeps them resident in shared memory and sweeps the bank segment with cta_group::2 MMAs.
- * Same outputs, tie rule and indices relative to b_row0 as fp_knn_search_items. */
+ * Same outputs, tie rule and indices relative to b_row0 as fp_knn_search_items.
+ * Sweep barrier (optional): items i, i + C, i + 2C, ... run on cluster i % C (C = fp_num_sms() / 2).  When the items of
+ * one wave [wC, wC + C) cover the same bank rows, set their `reserved` field to the number of items in that wave and
+ * pass a device uint64 `sync_counter` + `sync_tiles` > 0: every sync_tiles bank tiles (256 rows each) the clusters of a
+ * wave meet at a grid barrier, so the bank streams from HBM once per wave instead of once per cluster.  Every item
+ * of a wave must then have the same b_rows; items with reserved = 0 do not take part.  sync_counter may be NULL. */
 int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const float* q_sqnorm,
                              const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
                              int dim, const fp_knn_item* items, int num_items, int metric, int k,
-                             float* out_d, int64_t* out_i, void* stream);
+                             float* out_d, int64_t* out_i, uint64_t* sync_counter, int sync_tiles, void* stream);
 
 /* Experiment switches of the pair kernel (tools/k4_probe.py): bit 0 = skip the epilogue scan, bit 1 = stream the
  * queries instead of keeping them resident.  0 (default) in production. */

@@ -101,6 +101,9 @@ def main():
         elif v == "pair_stream_noscan":
             lib.fp_knn_set_flags(3)
             ms, tf = time_it(lambda: index.search_packed(q, qn), full)
+        elif v == "pair_nosync":
+            lib.fp_knn_set_flags(8)
+            ms, tf = time_it(lambda: index.search_packed(q, qn), full)
         elif v == "pair_ldtm":
             lib.fp_knn_set_flags(4)
             ms, tf = time_it(lambda: index.search_packed(q, qn), full)
