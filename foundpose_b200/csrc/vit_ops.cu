@@ -26,27 +26,29 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One thread per (patch, k-chunk of 14 contiguous pixels = one row of one channel of the patch).
+// One thread per (image row of one channel, patch column): 14 contiguous pixels -> 14 fp16 of that patch's im2col
+// row.  The patch column is the fastest-varying index, so a warp reads one contiguous stretch of an image row
+// (the first version had the patch row fastest: 56-byte reads 1680 bytes apart, 1.0 TB/s in ncu).
 __global__ void patchify_normalize_kernel(const float* __restrict__ img, __half* __restrict__ out,
                                           int B, int H, int W, int ps, int Kpad) {
   const int Hp = H / ps, Wp = W / ps;
-  const int rows_per_patch = 3 * ps;  // (channel, dy) pairs
-  const long total = static_cast<long>(B) * Hp * Wp * rows_per_patch;
+  const long total = static_cast<long>(B) * 3 * H * Wp;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(idx % rows_per_patch);
-    const long patch = idx / rows_per_patch;
-    const int c = r / ps, dy = r - c * ps;
-    const int px = static_cast<int>(patch % Wp);
-    const int py = static_cast<int>((patch / Wp) % Hp);
-    const int b = static_cast<int>(patch / (static_cast<long>(Wp) * Hp));
-    const float* src = img + ((static_cast<long>(b) * 3 + c) * H + (py * ps + dy)) * W + px * ps;
+    const int px = static_cast<int>(idx % Wp);
+    const long row = idx / Wp;                       // (b, c, y)
+    const int y = static_cast<int>(row % H);
+    const int c = static_cast<int>((row / H) % 3);
+    const int b = static_cast<int>(row / (3L * H));
+    const int py = y / ps, dy = y - py * ps;
+    const float* src = img + row * W + px * ps;
+    const long patch = (static_cast<long>(b) * Hp + py) * Wp + px;
     __half* dst = out + patch * Kpad + c * ps * ps + dy * ps;
     // (x - mean) / std exactly as torchvision's normalize (sub then div).
     for (int dx = 0; dx < ps; ++dx) dst[dx] = __float2half_rn((src[dx] - mean[c]) / stdv[c]);
-    if (r == 0) {
+    if (c == 0 && dy == 0) {
       for (int k = 3 * ps * ps; k < Kpad; ++k) out[patch * Kpad + k] = __float2half_rn(0.f);
     }
   }
@@ -219,7 +221,7 @@ int patchify_normalize(const float* img, __half* out, int B, int H, int W, int p
   FP_REQUIRE(H % ps == 0, "Input image height %d is not a multiple of patch height %d", H, ps);
   FP_REQUIRE(W % ps == 0, "Input image width %d is not a multiple of patch width: %d", W, ps);
   FP_REQUIRE(Kpad >= 3 * ps * ps, "patchify: Kpad too small");
-  const long total = static_cast<long>(B) * (H / ps) * (W / ps) * 3 * ps;
+  const long total = static_cast<long>(B) * 3 * H * (W / ps);
   ProfScope prof(PROF_VIT_MISC, stream, static_cast<double>(B) * 3 * H * W * 4 + static_cast<double>(B) * (H / ps) * (W / ps) * Kpad * 2);
   patchify_normalize_kernel<<<grid_for(total, 256), 256, 0, stream>>>(img, out, B, H, W, ps, Kpad);
   FP_CUDA_CHECK(cudaGetLastError());
