@@ -663,7 +663,8 @@ def spot_check(pipe, index, host_images, host_masks, sd, arch, layer, pdict, wl,
     crop = 0
     res = {}
     try:
-        st1 = ocheck.descriptor_stage(pipe, crop, host_images[crop], host_masks[crop].bool(), sd, arch, layer, pdict)
+        st1 = ocheck.descriptor_stage(pipe, crop, host_images[crop], host_masks[crop].bool(), sd, arch, layer, pdict,
+                                      desc=q_desc16)
         res["descriptor_rel_err"] = st1["rel_err"]
         res["query_points_equal"] = st1["points_equal"]
         assert st1["points_equal"] and st1["rel_err"] <= 1e-2, f"descriptor stage off: {st1['rel_err']}"

@@ -53,8 +53,10 @@ def _index_cpu(index: Any) -> Dict[str, torch.Tensor]:
 
 
 def descriptor_stage(pipe: Any, crop: int, image: torch.Tensor, mask: torch.Tensor, state_dict: Dict, arch: Any,
-                     layer: int, pca_dict: Optional[Dict], facet: str = "token", apply_norm: bool = True) -> Dict:
-    """Stage 1 for one crop.  image [3,H,W] fp32 CPU, mask [H,W] bool CPU."""
+                     layer: int, pca_dict: Optional[Dict], facet: str = "token", apply_norm: bool = True,
+                     desc: Optional[torch.Tensor] = None) -> Dict:
+    """Stage 1 for one crop.  image [3,H,W] fp32 CPU, mask [H,W] bool CPU.  `desc`: the [B*stride, d] tensor the
+    pipeline wrote its projected descriptors to (default: its own fp32 / fp16 buffer)."""
     size = (pipe.crop_w, pipe.crop_h)
     fmap = ovit.extract(state_dict, arch, image.unsqueeze(0), layer=layer, facet=facet,
                         apply_norm=apply_norm)["feature_maps"][0]
@@ -70,7 +72,7 @@ def descriptor_stage(pipe: Any, crop: int, image: torch.Tensor, mask: torch.Tens
     if pca_dict is not None:
         feats = opca.project_features(feats, [pca_dict]).contiguous()
     s = pipe.stride
-    src = pipe.proj32 if pipe.proj32 is not None else pipe.proj16
+    src = desc if desc is not None else (pipe.proj32 if pipe.proj32 is not None else pipe.proj16)
     ours = src[crop * s: crop * s + n, : feats.shape[1]].float().cpu()
     res["rel_err"] = float(torch.linalg.norm(ours - feats) / torch.linalg.norm(feats))
     cos = torch.nn.functional.cosine_similarity(ours, feats, dim=1)
