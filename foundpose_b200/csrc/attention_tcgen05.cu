@@ -340,17 +340,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
   const int last_valid = N - (num_kv - 1) * kBKV;
   const int last_len = (last_valid + 15) / 16 * 16;
 
+  // Issue mode (flags bit 14 = 0, default): ONE ISSUER WARP PER QUERY TILE - warp 1 issues every MMA of tile A
+  // (S_A(j+1), then PV_A(j)), warp 3 those of tile B - so that the two tiles' pipelines are independent and can run
+  // out of phase (tile B starts `skew` cycles late, flags bits 8-13 x 128): while one softmax warp of a sub-partition
+  // computes exponentials the other one sits in its serial TMEM-load / max / TMEM-store phases.  Bit 14 = 1 selects
+  // the round-1 split (warp 1 = S of both tiles, warp 3 = PV of both tiles), whose in-order loops re-align the tiles
+  // at every key block.  K / V / Q stages are released by both issuers in the per-tile mode (count 2).
+  const bool per_tile_issue = (flags & 0x4000) == 0;
+  const uint32_t release_count = per_tile_issue ? 2 : 1;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->q_full[s], 1);
-      mbar_init(&bars->q_empty[s], 1);
+      mbar_init(&bars->q_empty[s], release_count);
     }
     for (int s = 0; s < kKVStages; ++s) {
       mbar_init(&bars->k_full[s], 1);
-      mbar_init(&bars->k_empty[s], 1);
+      mbar_init(&bars->k_empty[s], release_count);
       mbar_init(&bars->v_full[s], 1);
-      mbar_init(&bars->v_empty[s], 1);
+      mbar_init(&bars->v_empty[s], release_count);
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(&bars->s_full[x], 1);
@@ -414,6 +422,75 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
           if (++stage == kKVStages) { stage = 0; phase ^= 1; }
           if (j == q_prefetch_at && it + static_cast<int>(gridDim.x) < num_items) load_q(it + gridDim.x, n + 1);
         }
+      }
+    } else if (per_tile_issue && (warp == 1 || warp == 3)) {
+      // ===== MMA issuer of ONE query tile: S_x(0), then per key block { S_x(j+1) ; O_x += P_x(j) V_j } =====
+      // (whole warp runs the loop with warp-uniform operands, one elected lane issues - see the note below)
+      const int x = (warp == 1) ? 0 : 1;
+      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + x * kQBytes));
+      const uint64_t kdesc0 = make_smem_desc_sw128(smem_u32(sK));
+      const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV));
+      constexpr uint32_t idesc_full = make_idesc_f16(kBQ, kBKV, 0, 0);
+      const uint32_t idesc_last = make_idesc_f16(kBQ, last_len, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(kBQ, kHD, 0, 1);   // B (=V) is MN-major
+      const uint32_t tS = tmem_base + kColS + x * kBKV;
+      const uint32_t tO = tmem_base + kColO + x * kHD;
+      const uint32_t tP = tmem_base + kColP + x * (kBKV / 2);   // 8 columns per 16 keys
+      int kstage = 0, vstage = 0;
+      uint32_t kphase = 0, vphase = 0;
+      uint32_t blk = 0;   // running count of key blocks processed by this CTA (barrier parity)
+      int n = 0;          // items done by this CTA: Q stage n & 1, phase (n >> 1) & 1
+      if (x == 1) {       // start tile B out of phase with tile A
+        const long long skew = static_cast<long long>((flags >> 8) & 0x3f) * 128;
+        const long long t0 = clock64();
+        while (clock64() - t0 < skew) {}
+      }
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
+        const int qs = n & 1;
+        mbar_wait(&bars->q_full[qs], (n >> 1) & 1);
+        const uint64_t qd = qdesc + static_cast<uint64_t>(qs * (2 * kQBytes / 16));
+        auto issue_s = [&](int j) {
+          const uint32_t idesc_s = (j == num_kv - 1) ? idesc_last : idesc_full;
+          mbar_wait(&bars->k_full[kstage], kphase);
+          mbar_wait(&bars->s_empty[x], ((blk + j) & 1) ^ 1);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint64_t kd = kdesc0 + static_cast<uint64_t>(kstage * (kKBytes / 16));
+#pragma unroll
+            for (int k = 0; k < kHD / 16; ++k) umma_f16_ss(tS, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+            umma_commit(&bars->s_full[x]);
+            umma_commit(&bars->k_empty[kstage]);
+            if (j == num_kv - 1) umma_commit(&bars->q_empty[qs]);   // this Q stage may be overwritten
+          }
+          __syncwarp();
+          if (++kstage == kKVStages) { kstage = 0; kphase ^= 1; }
+        };
+        issue_s(0);
+        for (int j = 0; j < num_kv; ++j) {
+          if (j + 1 < num_kv) issue_s(j + 1);
+          const uint32_t acc0 = j != 0;          // the first block of an item overwrites O
+          const int ksteps = (j == num_kv - 1) ? last_len / 16 : kBKV / 16;
+          mbar_wait(&bars->v_full[vstage], vphase);
+          mbar_wait(&bars->p_full[x], (blk + j) & 1);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint64_t vd = vdesc0 + static_cast<uint64_t>(vstage * (kVBytes / 16));
+            if (ksteps == kBKV / 16) {
+#pragma unroll
+              for (int k = 0; k < kBKV / 16; ++k)
+                umma_f16_ts(tO, tP + k * 8, vd + k * 128, idesc_pv, acc0 | (k != 0));
+            } else {
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                umma_f16_ts(tO, tP + k * 8, vd + k * 128, idesc_pv, acc0 | (k != 0));
+            }
+            umma_commit(&bars->pv_done[x]);
+            umma_commit(&bars->v_empty[vstage]);
+          }
+          __syncwarp();
+          if (++vstage == kKVStages) { vstage = 0; vphase ^= 1; }
+        }
+        blk += num_kv;
       }
     } else if (warp == 1) {
       // ===== MMA issuer 1: S_X(j) = Q_X K_j^T for both query tiles =====

@@ -12,8 +12,15 @@ import torch  # noqa: E402
 from foundpose_b200 import _native  # noqa: E402
 
 B, N, H = 64, 901, 16
-VARIANTS = [("1thr/row 24|24", 1), ("1thr/row 0|0", 2), ("1thr/row 16|16", 3), ("1thr/row 32|32", 4), ("2thr/row 0|0", 5),
-            ("2thr/row 16|16", 6), ("2thr/row 8|24", 7), ("default", 0)]
+# flags: bits 0-7 = kernel variant + 1 (0 = production), bits 8-13 = start skew of query tile B in units of 128 cycles,
+# bit 14 = round-1 issue split (S issuer / PV issuer) instead of one issuer warp per query tile
+OLD = 1 << 14
+VARIANTS = [("r1 split 24|24", 1 | OLD), ("per-tile skew0", 1), ("per-tile skew512", 1 | (4 << 8)),
+            ("per-tile skew1024", 1 | (8 << 8)), ("per-tile skew1536", 1 | (12 << 8)), ("per-tile skew2048", 1 | (16 << 8)),
+            ("per-tile skew3072", 1 | (24 << 8)), ("per-tile 32|32 s1024", 4 | (8 << 8)), ("per-tile 16|16 s1024", 3 | (8 << 8)),
+            ("default", 0)]
+if len(sys.argv) > 1:
+    VARIANTS = [v for v in VARIANTS if any(a in v[0] for a in sys.argv[1:])]
 g = torch.Generator().manual_seed(0)
 qkv = (torch.randn(B * N, 3 * H * 64, generator=g) * 1.5).half().cuda()
 lib = _native.load()
