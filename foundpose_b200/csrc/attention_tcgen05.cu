@@ -441,7 +441,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
       uint32_t blk = 0;   // running count of key blocks processed by this CTA (barrier parity)
       int n = 0;          // items done by this CTA: Q stage n & 1, phase (n >> 1) & 1
       if (x == 1) {       // start tile B out of phase with tile A
-        const long long skew = static_cast<long long>((flags >> 8) & 0x3f) * 128;
+        // default (no skew bits set): 1024 cycles, about half a key block of one tile
+        const long long skew = static_cast<long long>(((flags >> 8) & 0x3f) ? ((flags >> 8) & 0x3f) : 8) * 128;
         const long long t0 = clock64();
         while (clock64() - t0 < skew) {}
       }
