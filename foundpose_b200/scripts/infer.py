@@ -223,23 +223,41 @@ def infer(opts: InferOpts, repre_dir: Optional[str] = None, crops_path: Optional
         repre = make_synthetic_repre(extractor.arch.embed_dim, d, t, p, w, device) if rank == 0 else None
     repre = distributed.broadcast_object_repre(repre, src=0, device=device)
 
+    # Crop cameras (fx, fy, cx, cy per crop).  Real crops must bring the intrinsics of their virtual crop camera
+    # (the reference builds it per instance with misc.construct_crop_camera, scripts/infer.py:411-440): without them no
+    # coarse pose is emitted.  Only the synthetic mode falls back to a made-up camera.
+    crop_intrinsics: Optional[torch.Tensor] = None
     if crops_path is not None:
         blob = torch.load(crops_path, map_location="cpu")
         images, masks = blob["images"].float(), blob["masks"].bool()
+        if "intrinsics" in blob:
+            crop_intrinsics = torch.as_tensor(blob["intrinsics"], dtype=torch.float64).reshape(-1, 4)
+            if crop_intrinsics.shape[0] != images.shape[0]:
+                raise ValueError("crops blob: `intrinsics` needs one (fx, fy, cx, cy) row per crop")
+        else:
+            logger.warning("The crops blob has no `intrinsics` [P,4]: correspondences only, no coarse poses.")
     else:
         images = synthetic.make_crops(num_synthetic_crops, opts.crop_size, seed=1)
         masks = synthetic.make_masks(num_synthetic_crops, opts.crop_size, seed=2)
+        cam = default_crop_camera(opts.crop_size)
+        crop_intrinsics = torch.from_numpy(pnp_util.get_intrinsics_vector(cam)).reshape(1, 4).repeat(images.shape[0], 1)
     start, end = distributed.shard_range(images.shape[0], rank, world)
     images, masks = images[start:end].to(device), masks[start:end].to(device)
+    if crop_intrinsics is not None:
+        crop_intrinsics = crop_intrinsics[start:end].to(device).contiguous()
 
     grid_points = feature_util.generate_grid_points(grid_size=opts.crop_size, cell_size=opts.grid_cell_size).to(device)
     index, visual_words_knn_index, template_knn_indices = build_indices(repre, opts, device)
     logging.log_heading(logger, f"Object representation: {index.num_templates} templates, "
                                 f"{index.bank16.shape[0]} features, vertices: {len(repre.vertices)}")
     results: List[Dict[str, Any]] = []
-    camera_c2w = default_crop_camera(opts.crop_size)
-    intrinsics = torch.from_numpy(pnp_util.get_intrinsics_vector(camera_c2w)).to(device).reshape(1, 4)
     if batch > 0:
+        grid_n = grid_points.shape[0]
+        if opts.max_num_queries < grid_n:
+            # the reference sub-samples the query points per instance with torch.randperm (scripts/infer.py:483-485);
+            # the batched path keeps a fixed stride of grid points per crop
+            raise ValueError(f"max_num_queries={opts.max_num_queries} < {grid_n} grid points: use the per-crop path "
+                             "(batch=0), which sub-samples the query points like the reference")
         pipe = pipeline.CropBatchPipeline(extractor, index, repre.feat_raw_projectors, batch,
                                           crop_size=opts.crop_size, grid_cell_size=opts.grid_cell_size,
                                           top_n_templates=opts.match_top_n_templates,
@@ -255,15 +273,20 @@ def infer(opts: InferOpts, repre_dir: Optional[str] = None, crops_path: Optional
             out = pipe.run(img.contiguous(), msk.contiguous())
             # Coarse poses of all (crop, template) pairs of the batch in one launch.
             topn, kk = out.count.shape[1], out.coord_2d.shape[2]
-            poses = pnp_util.estimate_poses_batched(
-                out.coord_2d.reshape(batch * topn, kk, 2), out.coord_3d.reshape(batch * topn, kk, 3),
-                out.count.reshape(-1), intrinsics.expand(batch * topn, 4).contiguous(), opts.pnp_ransac_iter,
-                opts.pnp_inlier_thresh, opts.pnp_required_ransac_conf, problem_offset=(start + s) * topn)
-            best = pnp_util.select_best_poses(poses["success"], poses["num_inliers"], topn).cpu()
-            poses = {k: v.cpu() for k, v in poses.items()}
+            best = poses = None
+            if crop_intrinsics is not None:
+                intr = crop_intrinsics[s:e]
+                if e - s < batch:
+                    intr = torch.cat([intr, intr[:1].expand(batch - (e - s), 4)])
+                poses = pnp_util.estimate_poses_batched(
+                    out.coord_2d.reshape(batch * topn, kk, 2), out.coord_3d.reshape(batch * topn, kk, 3),
+                    out.count.reshape(-1), intr.repeat_interleave(topn, dim=0).contiguous(), opts.pnp_ransac_iter,
+                    opts.pnp_inlier_thresh, opts.pnp_required_ransac_conf, problem_offset=(start + s) * topn)
+                best = pnp_util.select_best_poses(poses["success"], poses["num_inliers"], topn).cpu()
+                poses = {k: v.cpu() for k, v in poses.items()}
             for b in range(e - s):
                 corresp = pipeline.outputs_to_corresp_list(out, b)
-                j = int(best[b])
+                j = int(best[b]) if best is not None else -1
                 results.append({"crop_id": start + s + b, "corresp": [
                     {k: v.cpu().clone() for k, v in c.items()} for c in corresp],
                     "best_coarse_pose": None if j < 0 else {
@@ -275,7 +298,11 @@ def infer(opts: InferOpts, repre_dir: Optional[str] = None, crops_path: Optional
             corresp, times = infer_instance(opts, extractor, repre, grid_points, images[i], masks[i],
                                             visual_words_knn_index, template_knn_indices)
             logger.info(f"Number of corresp: {[len(c['coord_2d']) for c in corresp]}")
-            coarse_poses, best_id = estimate_coarse_poses(opts, corresp, camera_c2w)
+            coarse_poses, best_id = [], 0
+            if crop_intrinsics is not None:
+                fx, fy, cx, cy = [float(v) for v in crop_intrinsics[i].tolist()]
+                camera_c2w = structs.PinholePlaneCameraModel(opts.crop_size[0], opts.crop_size[1], (fx, fy), (cx, cy))
+                coarse_poses, best_id = estimate_coarse_poses(opts, corresp, camera_c2w)
             results.append({"crop_id": start + i, "time": times,
                             "corresp": [{k: v.cpu() for k, v in c.items()} for c in corresp],
                             "coarse_poses": coarse_poses,

@@ -70,3 +70,29 @@ def test_unsorted_template_ids_use_the_permutation():
         assert int(a["template_id"]) == int(b["template_id"])
         assert torch.equal(a["nn_vertex_ids"].cpu(), b["nn_vertex_ids"])      # original feature ids
         assert torch.equal(a["coord_3d"].cpu(), b["coord_3d"])
+
+
+def test_real_crops_use_their_own_cameras_and_need_them_for_poses(tmp_path, monkeypatch):
+    """--crops blobs: coarse poses are computed in the per-crop camera the blob brings (`intrinsics` [P,4]); a blob
+    without cameras yields correspondences but no poses (no made-up camera for real data)."""
+    from foundpose_b200.scripts import infer
+
+    monkeypatch.setenv("FOUNDPOSE_SYNTHETIC_WEIGHTS", "5")
+    opts = infer.InferOpts(extractor_name="dinov2_version=tiny-test-reg_stride=14_facet=token_layer=2_norm=1",
+                           grid_cell_size=14.0, crop_size=(112, 112), match_top_n_templates=3,
+                           match_top_k_buddies=25, debug=False)
+    images = synthetic.make_crops(4, (112, 112), seed=1)
+    masks = synthetic.make_masks(4, (112, 112), seed=2)
+    with_cam, without_cam = str(tmp_path / "a.pt"), str(tmp_path / "b.pt")
+    intr = torch.tensor([[500.0 + i, 510.0 + i, 56.0, 57.0] for i in range(4)], dtype=torch.float64)
+    torch.save({"images": images, "masks": masks, "intrinsics": intr}, with_cam)
+    torch.save({"images": images, "masks": masks}, without_cam)
+    for batch in (0, 4):
+        res = infer.infer(opts, crops_path=with_cam, batch=batch, synthetic_bank=(12, 40, 128, 32))
+        assert len(res) == 4 and all("best_coarse_pose" in r for r in res)
+        res = infer.infer(opts, crops_path=without_cam, batch=batch, synthetic_bank=(12, 40, 128, 32))
+        assert len(res) == 4 and all(r["best_coarse_pose"] is None for r in res)
+        assert any(len(r["corresp"]) > 0 for r in res)
+    with pytest.raises(ValueError):
+        infer.infer(infer.InferOpts(**{**opts._asdict(), "max_num_queries": 10}), crops_path=with_cam, batch=4,
+                    synthetic_bank=(12, 40, 128, 32))
