@@ -239,7 +239,7 @@ def knn_search_items(q16, q_sqnorm, bank16, bank_sqnorm, items, num_items, metri
 def knn_search_pair_items(q16, q_sqnorm, bank16, bank_sqnorm, items, num_items, metric: int, k: int, out_d, out_i,
                           sync_counter: Optional[torch.Tensor] = None, sync_tiles: int = 0) -> None:
     """Pair kernel (cta_group::2, queries resident in shared memory); items hold up to 256 query rows.
-    sync_counter (int64 [1], device) + sync_tiles > 0 enable the sweep barrier of items whose 4th word is set."""
+    sync_counter (int64 [2], device) + sync_tiles > 0 enable the sweep barrier of items whose 4th word is set."""
     require_cuda(q16, "q16", torch.float16)
     require_cuda(bank16, "bank16", torch.float16)
     assert q16.shape[1] == bank16.shape[1]

@@ -519,6 +519,7 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0, qphase = 0;
       unsigned long long sync_expected = 0;
+      bool sync_on = sync_tiles > 0;
       for (int it = cluster_id; it < num_items; it += num_clusters) {
         const KnnItem item = items[it];
         if (item.q_rows <= 0 || item.b_rows <= 0) continue;
@@ -536,20 +537,25 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // once per cluster (ncu: 790 GB of DRAM reads per 57 600-query launch without it, L2 hit rate 57%).
         const unsigned long long participants = static_cast<unsigned long long>(item.pad);
         for (int t = 0; t < num_tiles; ++t) {
-          if (sync_tiles > 0 && participants > 0 && rank == 0 && (t % sync_tiles) == 0) {
+          if (sync_on && participants > 0 && rank == 0 && (t % sync_tiles) == 0) {
+            // sync_counter[0] = arrivals (monotonic), sync_counter[1] = "give up" flag.  The barrier is an
+            // optimisation, never a correctness requirement: if the other clusters do not show up within a few ms
+            // (the grid is not co-resident because another kernel holds SMs, or a cluster was delayed), this
+            // cluster raises the flag and every cluster lets its sweep run free for the rest of the launch.
             sync_expected += participants;
             asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(sync_counter) : "memory");
-            unsigned long long seen = 0;
+            unsigned long long seen = 0, quit = 0;
             uint32_t polls = 0;
             do {
               asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(sync_counter) : "memory");
               if (seen >= sync_expected) break;
-              __nanosleep(64);
-              if (++polls > (1u << 26)) {
-                printf("foundpose_b200: k-NN sweep barrier timed out (block %d: %llu of %llu)\n", blockIdx.x, seen,
-                       sync_expected);
-                __trap();
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(quit) : "l"(sync_counter + 1) : "memory");
+              if (quit != 0 || ++polls > 8192) {
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(sync_counter + 1), "l"(1ull) : "memory");
+                sync_on = false;
+                break;
               }
+              __nanosleep(100);
             } while (true);
           }
           for (int kb = 0; kb < num_kb; ++kb) {
@@ -696,7 +702,7 @@ int launch_knn_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnIte
   const int max_clusters = num_sms() / 2;
   const int clusters = num_items < max_clusters ? num_items : max_clusters;
   if (sync_counter == nullptr || (g_knn_flags & 8)) sync_tiles = 0;   // bit 3: experiment, sweeps run free
-  if (sync_tiles > 0) FP_CUDA_CHECK(cudaMemsetAsync(sync_counter, 0, sizeof(unsigned long long), stream));
+  if (sync_tiles > 0) FP_CUDA_CHECK(cudaMemsetAsync(sync_counter, 0, 2 * sizeof(unsigned long long), stream));
   ProfScope prof(PROF_KNN_PAIR, stream, 0.0);
   knn_pair_kernel<K><<<2 * clusters, kKnnThreads, L.smem_bytes, stream>>>(
       tmQ, tmX, items, num_items, dim, qnorm, xnorm, metric_ip, k_out, out_d, out_i, L, sync_counter, sync_tiles);

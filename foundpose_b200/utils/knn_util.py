@@ -215,7 +215,7 @@ class KNN:
             plan = (key, _native.knn_items_from_host(direct + split, dev), len(direct), len(split), chunks, chunk_rows,
                     torch.empty((rows, self.k), dtype=torch.float32, device=dev),
                     torch.empty((rows, self.k), dtype=torch.int64, device=dev),
-                    torch.zeros(1, dtype=torch.int64, device=dev))
+                    torch.zeros(2, dtype=torch.int64, device=dev))    # sweep barrier: arrivals, give-up flag
             self._pair_plan = plan
         _, items, n_direct, n_split, chunks, chunk_rows, buf_d, buf_i, sync = plan
         if n_split == 0:

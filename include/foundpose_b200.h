@@ -192,9 +192,11 @@ int fp_knn_search_items(const void* q_f16, int64_t q_rows_total, const float* q_
  * Same outputs, tie rule and indices relative to b_row0 as fp_knn_search_items.
  * Sweep barrier (optional): items i, i + C, i + 2C, ... run on cluster i % C (C = fp_num_sms() / 2).  When the items of
  * one wave [wC, wC + C) cover the same bank rows, set their `reserved` field to the number of items in that wave and
- * pass a device uint64 `sync_counter` + `sync_tiles` > 0: every sync_tiles bank tiles (256 rows each) the clusters of a
+ * pass a device `sync_counter` (TWO uint64 words, zeroed by the call) + `sync_tiles` > 0: every sync_tiles bank tiles (256 rows each) the clusters of a
  * wave meet at a grid barrier, so the bank streams from HBM once per wave instead of once per cluster.  Every item
- * of a wave must then have the same b_rows; items with reserved = 0 do not take part.  sync_counter may be NULL. */
+ * of a wave must then have the same b_rows; items with reserved = 0 do not take part.  The barrier is an optimisation
+ * only: a cluster that waits a few ms in vain (grid not co-resident) switches it off for the rest of the launch.
+ * sync_counter may be NULL. */
 int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const float* q_sqnorm,
                              const void* bank_f16, int64_t bank_rows_total, const float* bank_sqnorm,
                              int dim, const fp_knn_item* items, int num_items, int metric, int k,

@@ -302,3 +302,37 @@ def test_engine_cosine_visual_word_metric(soft):
         gap = (cos[ids][:-1] - cos[ids][1:]).min()
         if gap > 1e-3:
             assert torch.equal(out.template_ids[b].cpu(), ids)
+
+
+def test_pair_kernel_sweep_barrier_gives_up_instead_of_hanging():
+    """The sweep barrier of fp_knn_search_pair_items is an optimisation only: items that announce more participants
+    than there are clusters (a barrier that can never be satisfied - what a grid that is not co-resident looks like)
+    must switch it off after a bounded wait and still return the exact result."""
+    from foundpose_b200 import _native
+    from foundpose_b200.utils import knn_util
+    from oracle import knn as oknn
+
+    g = torch.Generator().manual_seed(12)
+    nq, nb, dim, k = 74 * 256, 9000, 64, 5
+    bank = synthetic.fp16_representable(torch.randn(nb, dim, generator=g))
+    q = synthetic.make_query_features(nq, dim, bank, seed=6)
+    bank16, q16 = bank.half().cuda(), q.half().cuda()
+    bn, qn = _native.row_sqnorm_f16(bank16), _native.row_sqnorm_f16(q16)
+    direct, split, chunks, _ = knn_util.plan_pair_items(nq, nb, _native.num_sms() // 2)
+    assert not split
+    items = _native.knn_items_from_host([it + (len(direct) + 1,) for it in direct], "cuda")   # one participant too many
+    d = torch.empty((nq, k), device="cuda")
+    i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    sync = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _native.knn_search_pair_items(q16, qn, bank16, bn, items, len(direct), 0, k, d, i, sync, 4)
+    torch.cuda.synchronize()
+    assert int(sync[1].item()) == 1                               # the give-up flag was raised
+    rd, ri = oknn.knn_l2(q[:2048], bank, k)
+    sure = oknn.topk_margin(q[:2048], bank, k) > 1e-4
+    assert torch.equal(i[:2048].cpu()[sure], ri[sure])
+    # and with the right participant count the flag stays down
+    items = _native.knn_items_from_host([it + (len(direct),) for it in direct], "cuda")
+    _native.knn_search_pair_items(q16, qn, bank16, bn, items, len(direct), 0, k, d, i, sync, 4)
+    torch.cuda.synchronize()
+    assert int(sync[1].item()) == 0 and int(sync[0].item()) > 0
+    assert torch.equal(i[:2048].cpu()[sure], ri[sure])
