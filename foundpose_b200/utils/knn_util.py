@@ -10,6 +10,7 @@ on the device of the query tensor, as the reference does (:102-104).
 
 import math
 import os
+import weakref
 from typing import Any, Optional, Tuple
 
 import torch
@@ -112,7 +113,7 @@ class KNN:
         """An index over already packed fp16 rows (a zero-copy view of an ObjectIndex segment)."""
         self = cls(k=k, metric=metric)
         self._bank16, self._bank_sqnorm = bank16, bank_sqnorm
-        self.index = self
+        self.index = weakref.proxy(self)     # `knn.index` as in the reference, without a reference cycle
         return self
 
     def fit(self, data: torch.Tensor) -> None:
@@ -123,7 +124,7 @@ class KNN:
         x = _pad64(data.detach().to(dev))
         self._bank16 = _native.convert_rows_f16(x, l2_normalize=(self.metric == "cosine"))
         self._bank_sqnorm = _native.row_sqnorm_f16(self._bank16)
-        self.index = self
+        self.index = weakref.proxy(self)
 
     def search(self, data: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Finds nearest neighbors; returns (distances, indices) of the k nearest neighbors."""
