@@ -594,21 +594,10 @@ def run_cuda_arm(args) -> None:
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        bank_cpu = cpu_bank_dict(bank, index.template_descs, index.idfs)
-        shipped = CpuReferencePath(wl, bank_cpu, full_depth=True)
-        t_full = time_cpu_path(shipped, args.cpu_crops, 1)
-        early = CpuReferencePath(wl, bank_cpu, full_depth=False)
-        t_early = time_cpu_path(early, max(1, args.cpu_crops // 2), 1)
-        tot = sum(a + b for a, b in t_full)
-        cpu_baseline = {
-            "value": len(t_full) / tot, "unit": "crops/s", "cores": cores, "kind": "port",
-            "sample": cpu_sample_text(shipped, len(t_full), cores),
-            "without_k4_value": len(t_full) / sum(a for a, _ in t_full),
-            "early_exit_without_k4_value": len(t_early) / sum(a for a, _ in t_early),
-            "early_exit_note": f"same without K4, only blocks 0..{layer} executed (the ViT work this repo's path does)",
-        }
+        try:
+            cpu_baseline = measure_cpu_baseline(wl, bank, index, arch, layer, args.cpu_crops)
+        except Exception as e:   # e.g. not enough host memory for the fp32 bank: the headline line must still appear
+            cpu_baseline = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
@@ -643,6 +632,25 @@ def run_cuda_arm(args) -> None:
         import torch.distributed as dist
 
         dist.destroy_process_group()
+
+
+def measure_cpu_baseline(wl: dict, bank: dict, index, arch, layer: int, n_crops: int) -> dict:
+    """The oracle port of the reference path on the host cores, on a bounded sample of the same workload."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bank_cpu = cpu_bank_dict(bank, index.template_descs, index.idfs)
+    shipped = CpuReferencePath(wl, bank_cpu, full_depth=True)
+    t_full = time_cpu_path(shipped, n_crops, 1)
+    early = CpuReferencePath(wl, bank_cpu, full_depth=False)
+    t_early = time_cpu_path(early, max(1, n_crops // 2), 1)
+    tot = sum(a + b for a, b in t_full)
+    return {
+        "value": len(t_full) / tot, "unit": "crops/s", "cores": cores, "kind": "port",
+        "sample": cpu_sample_text(shipped, len(t_full), cores),
+        "without_k4_value": len(t_full) / sum(a for a, _ in t_full),
+        "early_exit_without_k4_value": len(t_early) / sum(a for a, _ in t_early),
+        "early_exit_note": f"same without K4, only blocks 0..{layer} executed (the ViT work this repo's path does)",
+    }
 
 
 def read_json_key(name: str, key: str):
@@ -684,10 +692,9 @@ def spot_check(pipe, index, host_images, host_masks, sd, arch, layer, pdict, wl,
                                           wl["top_k"])
         res["end_to_end"] = e2e
         res["ok"] = True
-    except AssertionError as e:
+    except Exception as e:   # reported in the line (ok: false), never fatal for the measurement itself
         res["ok"] = False
-        res["error"] = str(e)
-        raise
+        res["error"] = f"{type(e).__name__}: {e}"
     finally:
         res["seconds"] = round(time.perf_counter() - t0, 2)
     return res
