@@ -31,6 +31,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace fp {
 
 static unsigned long long* g_attn_dbg = nullptr;   // timeline buffer (tools/attn_timeline.py)
@@ -702,6 +704,11 @@ int attention_f16(const __half* qkv, __half* out, int B, int N, int heads, cudaS
   // Kernel variants: (threads per row, share of the exponentials of tile A / tile B evaluated on
   // the FMA pipe, in pairs out of 64 per row and key block).  g_attn_flags (tools/attn_bench.py)
   // overrides the production choice: bits 0-7 = variant + 1.
+  static const int env_flags = []() {   // FOUNDPOSE_ATTN_FLAGS: same bits as attention_set_flags, for A/B runs of bench.py
+    const char* e = getenv("FOUNDPOSE_ATTN_FLAGS");
+    return e ? static_cast<int>(strtol(e, nullptr, 0)) : 0;
+  }();
+  if (g_attn_flags == 0 && env_flags != 0) g_attn_flags = env_flags;
   const int variant = (g_attn_flags & 0xff) ? (g_attn_flags & 0xff) - 1 : kDefaultVariant;
 #define FP_ATTN_LAUNCH(IDX, SPLIT, PA, PB)                                                              \
   case IDX: {                                                                                           \
