@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FP_B200_VERSION 100
+#define FP_B200_VERSION 200
 
 /* Last error message of the calling thread (never NULL). */
 const char* fp_last_error(void);
