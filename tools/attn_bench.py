@@ -18,7 +18,8 @@ OLD = 1 << 14
 VARIANTS = [("r1 split 24|24", 1 | OLD), ("per-tile skew0", 1), ("per-tile skew512", 1 | (4 << 8)),
             ("per-tile skew1024", 1 | (8 << 8)), ("per-tile skew1536", 1 | (12 << 8)), ("per-tile skew2048", 1 | (16 << 8)),
             ("per-tile skew3072", 1 | (24 << 8)), ("per-tile 32|32 s1024", 4 | (8 << 8)), ("per-tile 16|16 s1024", 3 | (8 << 8)),
-            ("default", 0)]
+            ("2thr/row 0|0 per-tile", 5), ("2thr/row 16|16 per-tile", 6), ("2thr/row 8|24 per-tile", 7),
+            ("2thr/row 16|16 r1 split", 6 | OLD), ("default", 0)]
 if len(sys.argv) > 1:
     VARIANTS = [v for v in VARIANTS if any(a in v[0] for a in sys.argv[1:])]
 g = torch.Generator().manual_seed(0)
