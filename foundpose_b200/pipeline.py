@@ -292,8 +292,10 @@ class CropBatchPipeline:
         d_vit = extractor.arch.embed_dim
         self.projector = None
         if projectors:
-            assert len(projectors) == 1, "a single PCA projector is supported on the batched path"
-            self.projector = projectors[0].device_state(dev)
+            from foundpose_b200.utils import projector_util
+
+            # a chain of projectors (project_features applies them in turn) collapses to one affine map: one GEMM
+            self.projector = projector_util.compose_projectors(list(projectors)).device_state(dev)
         rows = batch * self.stride
         f32, f16, i32 = torch.float32, torch.float16, torch.int32
         self.tokens = torch.empty((batch, self.hp * self.wp, d_vit), dtype=f32, device=dev)

@@ -148,6 +148,33 @@ class PCAProjector(Projector):
         return out[:, : st["d_out"]]
 
 
+def compose_projectors(projectors: List[Projector]) -> Projector:
+    """One PCA projector equal to applying `projectors` in turn (project_features, reference :71-88).
+
+    transform_i(x) = (x - m_i) C_i^T is affine, so the chain collapses to x A^T + b with A = C_n ... C_1 (float64):
+    the batched pipeline runs ONE GEMM whatever the number of projectors stored in repre.pth.  Returned as a
+    PCAProjector with components_ = A and mean_ chosen so that -mean . A^T = b (least squares; exact whenever b lies
+    in the row space of A, which holds for a chain of PCA projections)."""
+    if len(projectors) == 1:
+        return projectors[0]
+    a, b = None, None
+    for proj in projectors:
+        if not isinstance(proj, PCAProjector):
+            raise ValueError(f"Unknown projector type: {type(proj)}")
+        c = np.asarray(proj.pca.components_, dtype=np.float64)
+        m = np.asarray(proj.pca.mean_, dtype=np.float64)
+        if a is None:
+            a, b = c, -(m @ c.T)
+        else:
+            a, b = c @ a, (b - m) @ c.T
+    out = PCAProjector(n_components=a.shape[0], whiten=False)
+    state = _PCAState(n_components=a.shape[0])
+    state.components_ = a.astype(np.float32)
+    state.mean_ = (-np.linalg.lstsq(a, b, rcond=None)[0]).astype(np.float32)
+    out.pca = state
+    return out
+
+
 def project_features(feat_vectors: torch.Tensor, projectors: List[Projector], batch_size: int = 4096) -> torch.Tensor:
     """Projects (num_features, feat_dims) feature vectors with every projector in turn."""
     for projector in projectors:

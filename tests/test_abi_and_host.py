@@ -218,3 +218,28 @@ def test_pair_item_plan_covers_every_query_once_and_fills_the_tail_wave():
         q_pad = (len(split) // chunks) * 256 if split else 0
         assert sorted(o0 for *_, o0 in split) == sorted(c * q_pad + j * 256 for c in range(chunks if split else 0)
                                                         for j in range(len(split) // chunks))
+
+
+def test_projector_chain_composes_to_one_affine_map():
+    """project_features applies the projectors in turn (reference utils/projector_util.py:71-88); the batched pipeline
+    folds the chain into ONE PCA-shaped projector: same result to fp32 rounding."""
+    import numpy as np
+
+    from foundpose_b200 import synthetic
+    from foundpose_b200.utils import projector_util as pu
+
+    chain = [pu.projector_from_tensordict(synthetic.make_pca(128, 64, 1)),
+             pu.projector_from_tensordict(synthetic.make_pca(64, 32, 2)),
+             pu.projector_from_tensordict(synthetic.make_pca(32, 16, 3))]
+    one = pu.compose_projectors(chain)
+    assert one.pca.components_.shape == (16, 128)
+    x = np.random.RandomState(0).randn(40, 128)
+
+    def transform(p, v):
+        return (v - np.asarray(p.pca.mean_, dtype=np.float64)) @ np.asarray(p.pca.components_, dtype=np.float64).T
+
+    ref = x
+    for p in chain:
+        ref = transform(p, ref)
+    assert np.abs(transform(one, x) - ref).max() < 1e-6
+    assert pu.compose_projectors(chain[:1]) is chain[0]
