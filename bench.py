@@ -506,8 +506,12 @@ def run_cuda_arm(args) -> None:
             "bound": "tensor", "achieved": k4_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
             "frac": k4_tflops / tensor_peak,
             "traffic": read_json_key("r02_k4_traffic.json", "bytes_per_launch"),
-            "traffic_note": "DRAM read+write bytes of one launch (ncu --set full, profiles/r02_k4_traffic.json); "
-                            "algorithmic bytes of a launch = one bank sweep F*d*2 + queries + results",
+            "traffic_note": "DRAM read+write bytes of one launch (ncu --set full, profiles/r02_k4_traffic.json). "
+                            "SURVEY 8(d) counts F*d*2 per 128-query tile (450 tiles per launch = 3.5 TB); with the 74 "
+                            "clusters of a wave sweeping in lockstep the bank leaves HBM once per WAVE (3 waves + the "
+                            "split tail wave = 4 sweeps = 31.5 GB); algorithmic_bytes_per_launch below = ONE sweep + "
+                            "queries + results, the floor of a single-sweep schedule. The kernel is tensor-bound: DRAM "
+                            "is 1.4% busy",
             "algorithmic_flops_per_launch": flops_per_launch,
             "algorithmic_bytes_per_launch": F * index.dim_padded * 2 + B * stride * (index.dim_padded * 2 + k4 * 12),
             "peak_source": peak_src, "launches_per_step": kf["launches_per_step"], "avg_launch_ms": avg_ms,
