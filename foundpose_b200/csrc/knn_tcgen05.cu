@@ -28,11 +28,16 @@ namespace fp {
 
 namespace {
 
+int g_knn_flags = 0;      // experiment switches (fp_knn_set_flags), 0 in production
+
 constexpr int BQ = 128;   // query rows per item
 constexpr int BX = 256;   // bank rows per tile (128 x 256 x 16 UMMA: 96 B/clk of smem operand reads)
 constexpr int BKK = 64;   // K elements per stage
 constexpr int kStages = 4;
 constexpr int kMaxK = 16;
+// Candidate lists of the k > 1 scan: kCandCap (distance, index) pairs per epilogue thread, laid out [slot][256 threads]
+// (conflict-free) in the 16 KB that the half-merge uses at the end of an item.
+constexpr int kCandCap = 8;
 constexpr int kXnTiles = 4;                        // bank tiles per staged group of ||x||^2 (one barrier per group)
 constexpr int kXnSlot = kXnTiles * BX + kXnTiles * (BX / 32);   // floats per slot: the norms + the min of every 32-column chunk
 constexpr uint32_t kXnBytes = 2 * kXnSlot * 4;         // ||x||^2 of the current and the next group of tiles
@@ -97,7 +102,8 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 template <int K>
 __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32_t xn /* shared address */,
                                                uint32_t xn_min /* shared address: min ||x||^2 per 32 columns */,
-                                               int col_base, int metric_ip, TopK<K>& best) {
+                                               int col_base, int metric_ip, TopK<K>& best,
+                                               uint32_t cand /* shared address: this thread's candidate list */) {
   // dist = scale * <q,x> + ||x||^2 with scale = -2 (L2) or -1 (IP, where the staged norms are zero): one FFMA per
   // candidate, no per-element select on the metric.
   const float scale = metric_ip ? -1.0f : -2.0f;
@@ -173,8 +179,49 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32
           for (int i = 0; i < w; ++i) m[i] = fminf(m[2 * i], m[2 * i + 1]);
         }
         if (m[0] < best.d[K - 1]) {
+          // Candidates exist.  Inserting straight from the 32 registers costs one guarded 5-deep insert per element
+          // POSITION at which any of the warp's 32 rows has a candidate - while the lists warm up (the whole item
+          // for the short items of the HBM-bound pass) that is nearly all 32 positions, ~750 instructions per
+          // chunk.  Instead every row appends ITS candidates (usually 1-3) to a small shared-memory list and the
+          // warp then runs the insert body max-over-rows-of-count times.  Fallbacks to the direct loop: a list that
+          // is not full yet (threshold = +inf: every element is a candidate) and a row with more than kCandCap
+          // candidates in one chunk.
+          const float thr = best.d[K - 1];
+          bool direct = thr == INFINITY;
+          int cnt = 0;
+          if (!direct) {
+            uint32_t ptr = cand;   // this thread's slot 0: dist at cand + j * 1024, index 8 KB further
 #pragma unroll
-          for (int i = 0; i < 32; ++i) best.push(dist[i], col_base + c * 32 + i);
+            for (int i = 0; i < 32; ++i) {
+              if (dist[i] < thr) {
+                if (cnt < kCandCap) {
+                  asm volatile("st.shared.f32 [%0], %1;" ::"r"(ptr), "f"(dist[i]) : "memory");
+                  asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr + kCandCap * 1024), "r"(col_base + c * 32 + i) : "memory");
+                  ptr += 1024;
+                }
+                ++cnt;
+              }
+            }
+            direct = cnt > kCandCap;
+          }
+          if (__any_sync(__activemask(), direct)) {
+            if (direct) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) best.push(dist[i], col_base + c * 32 + i);
+            }
+            if (direct) cnt = 0;
+          }
+          // drain: same insert order as the direct loop (ascending index), so ties resolve identically
+          const int rounds = __reduce_max_sync(__activemask(), cnt);
+          for (int j = 0; j < rounds; ++j) {
+            if (j < cnt) {
+              float cd;
+              int ci;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cd) : "r"(cand + j * 1024) : "memory");
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ci) : "r"(cand + j * 1024 + kCandCap * 1024) : "memory");
+              best.push(cd, ci);
+            }
+          }
         }
       }
     }
@@ -216,6 +263,7 @@ __device__ __forceinline__ void merge_halves_and_store(TopK<K>& best, int half, 
                                                        float* __restrict__ out_d, int64_t* __restrict__ out_i) {
   float* merge_d = reinterpret_cast<float*>(merge_buf);
   int* merge_i = reinterpret_cast<int*>(merge_buf + BQ * kMaxK * 4);
+  if constexpr (K > 1) asm volatile("bar.sync 1, 256;" ::: "memory");   // the buffer held the scans' candidate lists
   if (half == 1) {
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -249,7 +297,7 @@ __global__ void __launch_bounds__(kKnnThreads, 1)
 knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
            const KnnItem* __restrict__ items, int num_items, int dim,
            const float* __restrict__ qnorm, const float* __restrict__ xnorm, int metric_ip,
-           int k_out, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+           int k_out, float* __restrict__ out_d, int64_t* __restrict__ out_i, int flags) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -349,6 +397,7 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const int half = (warp - 4) >> 2;
     const int r = sub * 32 + lane;
     const int et = threadIdx.x - 128;          // 0..255: the tile column whose ||x||^2 this thread stages
+    const uint32_t cand = smem_u32(merge_buf) + et * 4;   // candidate list of this thread (k > 1 scans)
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -367,10 +416,11 @@ knn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
+        if (!(flags & 1))   // experiment switch: epilogue skips the scan (fp_knn_set_flags bit 0)
         scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
                           smem_u32(xn_s + (grp & 1) * kXnSlot + tg * BX + half * (BX / 2)),
                           smem_u32(xn_s + (grp & 1) * kXnSlot + kXnTiles * BX + tg * (BX / 32) + half * (BX / 64)),
-                          col_base, metric_ip, best);
+                          col_base, metric_ip, best, cand);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -407,7 +457,7 @@ int launch_knn(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* it
   const int grid = num_items < num_sms() ? num_items : num_sms();
   ProfScope prof(PROF_KNN, stream, 0.0);
   knn_kernel<K><<<grid, kKnnThreads, kKnnSmem, stream>>>(tmQ, tmX, items, num_items, dim, qnorm,
-                                                        xnorm, metric_ip, k_out, out_d, out_i);
+                                                        xnorm, metric_ip, k_out, out_d, out_i, g_knn_flags);
   FP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -616,6 +666,7 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int half = (warp - 4) >> 2;
     const int r = sub * 32 + lane;
     const int et = threadIdx.x - 128;          // 0..255: the tile column whose ||x||^2 this thread stages
+    const uint32_t cand = smem_u32(merge_buf) + et * 4;   // candidate list of this thread (k > 1 scans)
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -646,7 +697,7 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
                             smem_u32(xn_s + (grp & 1) * kXnSlot + tg * BX + half * (BX / 2)),
                             smem_u32(xn_s + (grp & 1) * kXnSlot + kXnTiles * BX + tg * (BX / 32) + half * (BX / 64)),
-                            col_base, metric_ip, best);
+                            col_base, metric_ip, best, cand);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -678,7 +729,6 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   bit 1  stream the queries with the bank even when they would fit in shared memory
 //   bit 2  epilogue warps only read the accumulators out of TMEM (no arithmetic)
 //   bit 3  no sweep barrier: the clusters' bank sweeps run free
-int g_knn_flags = 0;
 
 template <int K>
 int launch_knn_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const KnnItem* items, int num_items,
