@@ -35,9 +35,10 @@ constexpr int BX = 256;   // bank rows per tile (128 x 256 x 16 UMMA: 96 B/clk o
 constexpr int BKK = 64;   // K elements per stage
 constexpr int kStages = 4;
 constexpr int kMaxK = 16;
-// Candidate lists of the k > 1 scan: kCandCap (distance, index) pairs per epilogue thread, laid out [slot][256 threads]
-// (conflict-free) in the 16 KB that the half-merge uses at the end of an item.
-constexpr int kCandCap = 8;
+// Candidate lists of the k > 1 scan: kCandCap distances per epilogue thread, laid out [slot][256 threads]
+// (conflict-free) in the 16 KB that the half-merge uses at the end of an item.  A list is filled from 16 columns at
+// a time, so it cannot overflow.
+constexpr int kCandCap = 16;
 constexpr int kXnTiles = 4;                        // bank tiles per staged group of ||x||^2 (one barrier per group)
 constexpr int kXnSlot = kXnTiles * BX + kXnTiles * (BX / 32);   // floats per slot: the norms + the min of every 32-column chunk
 constexpr uint32_t kXnBytes = 2 * kXnSlot * 4;         // ||x||^2 of the current and the next group of tiles
@@ -58,16 +59,23 @@ struct TopK {
   }
   // Sorted ascending; a later candidate with an equal distance never displaces an earlier one,
   // so ties resolve to the lower index (candidates arrive in ascending index order).
-  __device__ __forceinline__ void push(float cd, int ci) {
-    if (cd < d[K - 1]) {
+  // Every slot is a select of old values and the candidate (p[] is monotone because the list is sorted), so the
+  // K slots update independently: depth 3 instead of a K-deep chain of conditional swaps, and a candidate that
+  // does not belong in the list (+inf for an idle lane) is a no-op without a guard branch.
+  __device__ __forceinline__ void insert(float cd, int ci) {
+    bool p[K];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        if (cd < d[j]) {
-          const float td = d[j]; d[j] = cd; cd = td;
-          const int ti = i[j]; i[j] = ci; ci = ti;
-        }
-      }
+    for (int j = 0; j < K; ++j) p[j] = cd < d[j];
+#pragma unroll
+    for (int j = K - 1; j >= 1; --j) {
+      d[j] = p[j - 1] ? d[j - 1] : (p[j] ? cd : d[j]);
+      i[j] = p[j - 1] ? i[j - 1] : (p[j] ? ci : i[j]);
     }
+    d[0] = p[0] ? cd : d[0];
+    i[0] = p[0] ? ci : i[0];
+  }
+  __device__ __forceinline__ void push(float cd, int ci) {
+    if (cd < d[K - 1]) insert(cd, ci);
   }
   // Lexicographic (distance, index) insert: used when merging lists whose index ranges interleave.
   __device__ __forceinline__ void push_lex(float cd, int ci) {
@@ -99,6 +107,51 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ float min16(const float* d) {
+  const float a = fminf(fminf(d[0], d[1]), d[2]);
+  const float b = fminf(fminf(d[3], d[4]), d[5]);
+  const float c = fminf(fminf(d[6], d[7]), d[8]);
+  const float e = fminf(fminf(d[9], d[10]), d[11]);
+  const float f = fminf(fminf(d[12], d[13]), d[14]);
+  return fminf(fminf(fminf(fminf(a, b), c), fminf(e, f)), d[15]);
+}
+
+// Inserts the candidates (distance < current k-th best) among 16 consecutive columns of this thread's row into its
+// sorted list.  Inserting straight from the registers costs one insert per column POSITION at which any of the
+// warp's 32 rows has a candidate - while the lists warm up (the whole sweep for the short sweeps of the HBM-bound
+// pass) that is nearly all of them.  Instead every row appends ITS candidates (usually 0-2) to a small list in
+// shared memory - four predicated instructions per column, no branches; which columns they were is a 16-bit mask -
+// and the warp then runs the insert max-over-rows-of-count times, idle rows inserting +inf.  Same insert order as
+// a scan in column order (ascending index), so ties resolve identically.  The warp must be converged.
+template <int K>
+__device__ __forceinline__ void insert_candidates(const float* dist, int idx0, TopK<K>& best, uint32_t cand) {
+  const float thr = best.d[K - 1];
+  uint32_t ptr = cand, mask = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.lt.f32 p, %2, %3;\n"
+        "@p st.shared.f32 [%0], %2;\n"
+        "@p or.b32 %1, %1, %4;\n"
+        "@p add.u32 %0, %0, 1024;\n"
+        "}"
+        : "+r"(ptr), "+r"(mask)
+        : "f"(dist[i]), "f"(thr), "r"(1u << i)
+        : "memory");
+  }
+  const int rounds = __reduce_max_sync(0xffffffffu, __popc(mask));
+  for (int j = 0; j < rounds; ++j) {
+    float cd;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cd) : "r"(cand + j * 1024) : "memory");
+    const int bit = __ffs(mask) - 1;
+    cd = mask ? cd : INFINITY;
+    mask &= mask - 1;
+    best.insert(cd, idx0 + bit);
+  }
+}
+
 template <int K>
 __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32_t xn /* shared address */,
                                                uint32_t xn_min /* shared address: min ||x||^2 per 32 columns */,
@@ -107,6 +160,7 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32
   // dist = scale * <q,x> + ||x||^2 with scale = -2 (L2) or -1 (IP, where the staged norms are zero): one FFMA per
   // candidate, no per-element select on the metric.
   const float scale = metric_ip ? -1.0f : -2.0f;
+  __syncwarp();   // the warp-wide votes and the .sync.aligned TMEM loads below need the 32 rows converged
 #pragma unroll 1
   for (int c = 0; c < BX / 64; ++c) {
     uint32_t v[32];
@@ -129,7 +183,8 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32
         m[6] = fmaxf(fmaxf(m[6], m[7]), m[8]);
         m[9] = fmaxf(m[9], m[10]);
         const float smax = fmaxf(fmaxf(fmaxf(m[0], m[3]), m[6]), m[9]);
-        if (fmaf(scale, smax, lds_f1(xn_min + c * 4)) >= best.d[K - 1]) continue;
+        // (warp-uniform: the rows of a warp stay converged for the collectives of the insert below)
+        if (!__any_sync(0xffffffffu, fmaf(scale, smax, lds_f1(xn_min + c * 4)) < best.d[K - 1])) continue;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 n4 = lds_f4(xn + (c * 32 + g * 4) * 4);
@@ -169,60 +224,13 @@ __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32
           best.i[0] = col_base + c * 32 + idx[0];
         }
       } else {
-        // Cheap prefilter: skip the chunk when nothing beats the current k-th best.
-        float m[16];   // min as a tree (depth 5), not a 31-deep dependent chain
-#pragma unroll
-        for (int i = 0; i < 16; ++i) m[i] = fminf(dist[2 * i], dist[2 * i + 1]);
-#pragma unroll
-        for (int w = 8; w >= 1; w >>= 1) {
-#pragma unroll
-          for (int i = 0; i < w; ++i) m[i] = fminf(m[2 * i], m[2 * i + 1]);
-        }
-        if (m[0] < best.d[K - 1]) {
-          // Candidates exist.  Inserting straight from the 32 registers costs one guarded 5-deep insert per element
-          // POSITION at which any of the warp's 32 rows has a candidate - while the lists warm up (the whole item
-          // for the short items of the HBM-bound pass) that is nearly all 32 positions, ~750 instructions per
-          // chunk.  Instead every row appends ITS candidates (usually 1-3) to a small shared-memory list and the
-          // warp then runs the insert body max-over-rows-of-count times.  Fallbacks to the direct loop: a list that
-          // is not full yet (threshold = +inf: every element is a candidate) and a row with more than kCandCap
-          // candidates in one chunk.
-          const float thr = best.d[K - 1];
-          bool direct = thr == INFINITY;
-          int cnt = 0;
-          if (!direct) {
-            uint32_t ptr = cand;   // this thread's slot 0: dist at cand + j * 1024, index 8 KB further
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (dist[i] < thr) {
-                if (cnt < kCandCap) {
-                  asm volatile("st.shared.f32 [%0], %1;" ::"r"(ptr), "f"(dist[i]) : "memory");
-                  asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr + kCandCap * 1024), "r"(col_base + c * 32 + i) : "memory");
-                  ptr += 1024;
-                }
-                ++cnt;
-              }
-            }
-            direct = cnt > kCandCap;
-          }
-          if (__any_sync(__activemask(), direct)) {
-            if (direct) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) best.push(dist[i], col_base + c * 32 + i);
-            }
-            if (direct) cnt = 0;
-          }
-          // drain: same insert order as the direct loop (ascending index), so ties resolve identically
-          const int rounds = __reduce_max_sync(__activemask(), cnt);
-          for (int j = 0; j < rounds; ++j) {
-            if (j < cnt) {
-              float cd;
-              int ci;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cd) : "r"(cand + j * 1024) : "memory");
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ci) : "r"(cand + j * 1024 + kCandCap * 1024) : "memory");
-              best.push(cd, ci);
-            }
-          }
-        }
+        // The k-th best bounds what can enter the list.  Test the two 16-column halves of the chunk (min trees of
+        // 3-input minima) and only where some row of the warp has a candidate run the insert for that half.
+        const int idx0 = col_base + c * 32;
+        const float h0 = min16(dist);
+        const float h1 = min16(dist + 16);
+        if (__any_sync(0xffffffffu, h0 < best.d[K - 1])) insert_candidates<K>(dist, idx0, best, cand);
+        if (__any_sync(0xffffffffu, h1 < best.d[K - 1])) insert_candidates<K>(dist + 16, idx0 + 16, best, cand);
       }
     }
   }

@@ -15,11 +15,11 @@ def main():
     from foundpose_b200.utils import knn_util
 
     dev = torch.device("cuda")
-    rows, dim = 10000 * 1024, 384
+    rows, dim = int(os.environ.get("KNN_PROBE_TEMPLATES", "10000")) * 1024, 384
     bank = torch.empty(rows, dim, device=dev, dtype=torch.float16)
     for s0 in range(0, rows, 1 << 20):
         bank[s0:s0 + (1 << 20)] = torch.randn(min(1 << 20, rows - s0), dim, device=dev, dtype=torch.float16)
-    knn = knn_util.KNN.from_packed(bank, _native.row_sqnorm_f16(bank), k=5, metric="l2")
+    knn = knn_util.KNN.from_packed(bank, _native.row_sqnorm_f16(bank), k=int(os.environ.get("KNN_PROBE_K", "5")), metric="l2")
     q = torch.randn(128, dim, device=dev)
     for _ in range(6):
         knn.search(q)
