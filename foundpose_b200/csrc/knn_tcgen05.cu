@@ -39,6 +39,7 @@ constexpr int kMaxK = 16;
 // (conflict-free) in the 16 KB that the half-merge uses at the end of an item.  A list is filled from 16 columns at
 // a time, so it cannot overflow.
 constexpr int kCandCap = 16;
+static_assert(kCandCap * 256 * 4 <= BQ * kMaxK * 8, "candidate lists must fit the half-merge buffer");
 constexpr int kXnTiles = 4;                        // bank tiles per staged group of ||x||^2 (one barrier per group)
 constexpr int kXnSlot = kXnTiles * BX + kXnTiles * (BX / 32);   // floats per slot: the norms + the min of every 32-column chunk
 constexpr uint32_t kXnBytes = 2 * kXnSlot * 4;         // ||x||^2 of the current and the next group of tiles
