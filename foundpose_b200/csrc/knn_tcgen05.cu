@@ -695,14 +695,18 @@ knn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const int col_base = t * BX + half * (BX / 2);
-        if (L.flags & 4) {   // experiment: TMEM reads only
+#ifdef FP_KNN_EXPERIMENTS   // make EXTRA=-DFP_KNN_EXPERIMENTS: TMEM reads only (fp_knn_set_flags bit 2); costs registers
+        if (L.flags & 4) {
+#pragma unroll 1
           for (int c = 0; c < BX / 64; ++c) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * BX + half * (BX / 2) + c * 32, v);
             tmem_ld_wait();
             if (__uint_as_float(v[0]) + __uint_as_float(v[31]) == 1.2345e30f) best.d[0] = 0.f;   // keep the load alive
           }
-        } else if (!(L.flags & 1))
+        } else
+#endif
+        if (!(L.flags & 1))
           scan_tile_half<K>(tmem_base + lane_addr + acc * BX + half * (BX / 2), item.b_rows - col_base,
                             smem_u32(xn_s + (grp & 1) * kXnSlot + tg * BX + half * (BX / 2)),
                             smem_u32(xn_s + (grp & 1) * kXnSlot + kXnTiles * BX + tg * (BX / 32) + half * (BX / 64)),

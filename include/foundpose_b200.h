@@ -202,8 +202,9 @@ int fp_knn_search_pair_items(const void* q_f16, int64_t q_rows_total, const floa
                              int dim, const fp_knn_item* items, int num_items, int metric, int k,
                              float* out_d, int64_t* out_i, uint64_t* sync_counter, int sync_tiles, void* stream);
 
-/* Experiment switches of the pair kernel (tools/k4_probe.py): bit 0 = skip the epilogue scan, bit 1 = stream the
- * queries instead of keeping them resident.  0 (default) in production. */
+/* Experiment switches of the k-NN kernels (tools/k4_probe.py, tools/knn_hbm_noscan.py): bit 0 = skip the epilogue scan,
+ * bit 1 = stream the queries instead of keeping them resident, bit 3 = no sweep barrier; bit 2 (TMEM reads only) exists
+ * only in builds with -DFP_KNN_EXPERIMENTS.  0 (default) in production. */
 int fp_knn_set_flags(int flags);
 
 /* ---- crop stage in front of the extractor ------------------------- */

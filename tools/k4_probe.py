@@ -104,7 +104,7 @@ def main():
         elif v == "pair_nosync":
             lib.fp_knn_set_flags(8)
             ms, tf = time_it(lambda: index.search_packed(q, qn), full)
-        elif v == "pair_ldtm":
+        elif v == "pair_ldtm":   # TMEM reads only: needs a library built with `make EXTRA=-DFP_KNN_EXPERIMENTS`
             lib.fp_knn_set_flags(4)
             ms, tf = time_it(lambda: index.search_packed(q, qn), full)
         elif v == "one_cta":
