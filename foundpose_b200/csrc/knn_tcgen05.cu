@@ -91,12 +91,7 @@ struct TopK {
 };
 
 
-// One epilogue thread's share of a 128 x 256 distance tile: its query row (TMEM lane) x one half (128) of the
-// tile's bank columns, starting at TMEM address `taddr`.  `ncols` = valid columns in this half (may be <= 0),
-// `xn` = ||x||^2 of the half's 128 columns STAGED IN SHARED MEMORY by the epilogue warps one tile ahead (a global
-// load per 32-column chunk on the critical path of every tile cost more than the chunk's arithmetic),
-// `col_base` = index of the half's first column relative to the item's segment.
-// L2: ||x||^2 - 2<q,x> (||q||^2 is added once per item); IP: -<q,x>.
+// Shared-memory loads by 32-bit shared address (pointers that went through uintptr_t arithmetic compile to generic loads).
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -153,6 +148,12 @@ __device__ __forceinline__ void insert_candidates(const float* dist, int idx0, T
   }
 }
 
+// One epilogue thread's share of a 128 x 256 distance tile: its query row (TMEM lane) x one half (128) of the
+// tile's bank columns, starting at TMEM address `taddr`.  `ncols` = valid columns in this half (may be <= 0),
+// `xn` = ||x||^2 of the half's 128 columns STAGED IN SHARED MEMORY by the epilogue warps one tile ahead (a global
+// load per 32-column chunk on the critical path of every tile cost more than the chunk's arithmetic),
+// `col_base` = index of the half's first column relative to the item's segment.
+// L2: ||x||^2 - 2<q,x> (||q||^2 is added once per item); IP: -<q,x>.
 template <int K>
 __device__ __forceinline__ void scan_tile_half(uint32_t taddr, int ncols, uint32_t xn /* shared address */,
                                                uint32_t xn_min /* shared address: min ||x||^2 per 32 columns */,
