@@ -5,7 +5,7 @@
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
 
 Default workload = BASELINE.json configs[2], the configuration the north-star target is quoted on:
-one "step" = 512 synthetic 420x420 crops (8 micro-batches of 64) through the whole path
+one "step" = 512 synthetic 420x420 crops (2 micro-batches of 256) through the whole path
 
     ViT-L/14 (blocks 0..9) -> mask filter -> sampling -> PCA 1024->384 -> visual-word 3-NN -> tf-idf ->
     cosine (bag-of-words) scores against 10 000 template descriptors -> top-5 templates -> 2 x 5 1-NN searches ->
@@ -37,9 +37,10 @@ import torch  # noqa: E402
 VITL = "dinov2_vitl14"
 WORKLOADS = {
     # BASELINE.json configs[2]: the north-star configuration (default at N=1 and for the scaling run).
-    "config3": dict(batch=64, crops_per_step=512, vit=VITL, templates=10000, patches=1024, dim=384, pca=True,
+    "config3": dict(batch=256, crops_per_step=512, vit=VITL, templates=10000, patches=1024, dim=384, pca=True,
                     words=2048, top_n=5, top_k=300, k4=5, cpu_k4_fraction=0.1,
-                    desc="configs[2]: batch=512 synthetic 420x420 crops per step (8 micro-batches of 64), ViT-L/14 "
+                    desc="configs[2]: batch=512 synthetic 420x420 crops per step (2 micro-batches of 256; the full-bank "
+                         "search is launched per 64 crops = 57 600 queries), ViT-L/14 "
                          "layer 9 + PCA 1024->384 + tf-idf BoW scoring of 10k templates + top-5 retrieval + cyclic "
                          "buddies + brute-force 5-NN of all 900 queries per crop vs the whole 10k-template x "
                          "1024-patch x 384-d bank (10.24M rows)"),
@@ -362,6 +363,10 @@ def run_cuda_arm(args) -> None:
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.load()
     wl = WORKLOADS[args.workload]
+    if os.environ.get("FP_BENCH_MICRO_BATCH"):      # experiment: crops per micro-batch (must divide crops_per_step)
+        wl = dict(wl, batch=int(os.environ["FP_BENCH_MICRO_BATCH"]))
+        wl["desc"] = wl["desc"].replace("2 micro-batches of 256", "%d micro-batches of %d" % (wl["crops_per_step"] // wl["batch"], wl["batch"]))
+        assert wl["crops_per_step"] % wl["batch"] == 0
     B = wl["batch"]
     n_micro = wl["crops_per_step"] // B
     arch, opts = vit_arch_and_layer(wl["vit"])
@@ -381,8 +386,12 @@ def run_cuda_arm(args) -> None:
     # Query descriptors of a whole step (the K4 search reads a micro-batch's slice right after it is produced).
     q_all = torch.zeros((n_micro, B * stride, index.dim_padded), dtype=torch.float16, device=dev)
     qn_all = torch.zeros((n_micro, B * stride), dtype=torch.float32, device=dev)
-    k4_d = [None] * n_micro
-    k4_i = [None] * n_micro
+    # The full-bank search is launched per K4_CROPS crops (57 600 queries: 3 whole waves of 74 clusters + a split tail
+    # wave - the launch shape the ncu evidence describes), whatever the micro-batch of the rest of the path.
+    k4_crops = min(B, 64)
+    k4_rows = k4_crops * stride
+    k4_d = [torch.zeros((B * stride, max(k4, 1)), dtype=torch.float32, device=dev) for _ in range(n_micro)]
+    k4_i = [torch.zeros((B * stride, max(k4, 1)), dtype=torch.int64, device=dev) for _ in range(n_micro)]
 
     # Inputs: one pool of n_micro micro-batches (>= 2), different crops per rank.  512 crops = 1.08 GB per step,
     # far larger than the 126 MB L2.
@@ -420,7 +429,10 @@ def run_cuda_arm(args) -> None:
         out = pipe.run(images, masks, desc_out=q_all[m])
         if with_k4:
             # ||q||^2 of this micro-batch's rows were computed by the engine (q_sqnorm); K4 = all queries x all rows.
-            k4_d[m], k4_i[m] = k4_index.search_packed(q_all[m], pipe.engine.q_sqnorm)
+            for r0 in range(0, B * stride, k4_rows):
+                d, i = k4_index.search_packed(q_all[m][r0:r0 + k4_rows], pipe.engine.q_sqnorm[r0:r0 + k4_rows])
+                k4_d[m][r0:r0 + k4_rows].copy_(d)      # the search returns its plan's buffers, reused by the next launch
+                k4_i[m][r0:r0 + k4_rows].copy_(i)
         return out
 
     def step_resident(i: int, with_k4: bool = bool(k4)) -> None:
@@ -498,7 +510,7 @@ def run_cuda_arm(args) -> None:
     if k4:
         kf = fam["knn_full_bank"]
         launches = max(kf["launches_per_step"], 1)
-        flops_per_launch = 2.0 * B * stride * F * index.dim_padded
+        flops_per_launch = 2.0 * k4_rows * F * index.dim_padded
         avg_ms = kf["ms_per_step"] / launches
         k4_tflops = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
         roofline = {
@@ -513,7 +525,7 @@ def run_cuda_arm(args) -> None:
                             "queries + results, the floor of a single-sweep schedule. The kernel is tensor-bound: DRAM "
                             "is 1.4% busy",
             "algorithmic_flops_per_launch": flops_per_launch,
-            "algorithmic_bytes_per_launch": F * index.dim_padded * 2 + B * stride * (index.dim_padded * 2 + k4 * 12),
+            "algorithmic_bytes_per_launch": F * index.dim_padded * 2 + k4_rows * (index.dim_padded * 2 + k4 * 12),
             "peak_source": peak_src, "launches_per_step": kf["launches_per_step"], "avg_launch_ms": avg_ms,
             "share_of_step": kf["ms_per_step"] / fam_ms if fam_ms > 0 else None,
         }
@@ -614,8 +626,7 @@ def run_cuda_arm(args) -> None:
                        "parallelism": f"crops sharded over {world} GPU(s), bank replicated"
                        + (f" (distributed.broadcast_object_repre over NCCL at init: {t_bcast:.2f} s)" if world > 1 else ""),
                        "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB of crops+masks per step, "
-                                    f"{n_pool} rotating micro-batch inputs, ~1.3 GB of activations rewritten per "
-                                    "micro-batch" + (f", {F * index.dim_padded * 2 / 1e9:.1f} GB bank swept by K4" if k4 else "")},
+                                    f"{n_pool} rotating micro-batch inputs, ~20 MB of activations rewritten per crop" + (f", {F * index.dim_padded * 2 / 1e9:.1f} GB bank swept by K4" if k4 else "")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "wall_s": e2e_wall},
@@ -629,7 +640,7 @@ def run_cuda_arm(args) -> None:
             kf = fam["knn_full_bank"]
             line["k4"] = {"tflops": roofline["achieved"], "frac_of_tensor_peak": roofline["frac"],
                           "ms_per_step": kf["ms_per_step"], "flops_per_crop": 2.0 * stride * F * index.dim_padded,
-                          "k": k4, "queries_per_launch": B * stride, "bank_rows": F}
+                          "k": k4, "queries_per_launch": k4_rows, "bank_rows": F}
         line.update(extras)
         emit_line(line)
     if world > 1:

@@ -6,7 +6,8 @@
     ncu --profile-from-start off --set full --clock-control none --import-source on \
         -o gpurun_out/prof_step python tools/profile_step.py --micro 1
 
-One micro-batch = 64 crops through the whole path of the workload (config3: incl. the full-bank search K4).
+One micro-batch = `batch` crops of the workload (config3: 256) through the whole path, incl. the full-bank search K4
+(launched per 64 crops).
 Numbers printed under ncu are never bench values; this script prints none.
 """
 import argparse
@@ -47,10 +48,13 @@ def main() -> None:
     images = [synthetic.make_crops(B, (420, 420), seed=100 + s).to(dev) for s in range(2)]
     masks = torch.ones(B, 420, 420, dtype=torch.uint8, device=dev)
 
+    k4_rows = min(B, 64) * pipe.stride     # the full-bank search is launched per 64 crops, as in bench.py
+
     def micro(i: int) -> None:
         pipe.run(images[i % 2], masks)
         if k4_index is not None:
-            k4_index.search_packed(pipe.proj16, pipe.engine.q_sqnorm)
+            for r0 in range(0, B * pipe.stride, k4_rows):
+                k4_index.search_packed(pipe.proj16[r0:r0 + k4_rows], pipe.engine.q_sqnorm[r0:r0 + k4_rows])
 
     for i in range(args.warmup):
         micro(i)
